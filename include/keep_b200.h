@@ -1,0 +1,159 @@
+/*
+ * keep_b200 C ABI — the drop-in boundary of the B200-native KEEP zero-shot WSI inference path.
+ *
+ * The reference (MAGIC-AI4Med/KEEP) is pure Python/PyTorch and has no FFI of its own; what this
+ * library replaces is the arithmetic behind three Python-level call sites:
+ *
+ *   KEEPModel.encode_image   quick_start/keep_inference.py:54-58   -> keepb200_encode_image
+ *   KEEPModel.encode_text    quick_start/keep_inference.py:60-62   -> keepb200_encode_text
+ *   tile x prompt similarity WSI_evaluation/detection_utils.py:90-93,
+ *                            subtyping_utils.py:69-72, segment_utils.py:46-49,
+ *                            quick_start/keep_inference.py:104      -> keepb200_similarity
+ *   prompt screening         WSI_evaluation/utils.py:107-146       -> keepb200_prompt_scores
+ *   refine_seg               detection_utils.py:39-74, subtyping_utils.py:38-65,
+ *                            segment_utils.py:63-89                 -> keepb200_refine
+ *
+ * The Python host mirror (keep_b200/modeling_keep.py, keep_b200/wsi.py) binds these with ctypes;
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer that carries tensor data is a DEVICE pointer owned by the caller (e.g. a torch
+ *     allocation), unless the parameter is documented as a host pointer;
+ *   - all calls are asynchronous on the CUDA stream that is passed (a cudaStream_t cast to void*;
+ *     NULL = the legacy default stream);
+ *   - return value 0 = success, negative = error (KEEPB200_ERR_*); nothing throws across the boundary;
+ *     keepb200_last_error() returns a thread-local message for the last failing call;
+ *   - one handle per device and per thread of control (a handle is not thread-safe);
+ *   - after keepb200_finalize() the library performs no hidden allocations: activations live in the
+ *     workspace the caller passes, sized by keepb200_workspace_bytes().
+ *   - there is no CPU fallback anywhere: without a CUDA device of compute capability 10.x every
+ *     compute entry point fails.
+ */
+#ifndef KEEP_B200_H_
+#define KEEP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KEEPB200_ABI_VERSION 1
+
+#define KEEPB200_OK 0
+#define KEEPB200_ERR_ARG (-1)
+#define KEEPB200_ERR_CUDA (-2)
+#define KEEPB200_ERR_STATE (-3)
+#define KEEPB200_ERR_WORKSPACE (-4)
+
+/* operand dtype of the tensor-core path (accumulation, residual stream, LayerNorm, softmax are fp32) */
+#define KEEPB200_FP16 0
+#define KEEPB200_BF16 1
+
+/* tile layouts accepted by keepb200_encode_image */
+#define KEEPB200_TILES_F32_NCHW 0 /* float [B,3,H,W], already ImageNet-normalised (keep_inference.py:88-93) */
+#define KEEPB200_TILES_U8_NHWC 1  /* uint8 [B,H,W,3] raw RGB; ToTensor+Normalize fused into the patch gather */
+
+/* ops for keepb200_workspace_bytes */
+#define KEEPB200_OP_ENCODE_IMAGE 0
+#define KEEPB200_OP_ENCODE_TEXT 1
+
+/* Model geometry. Mirrors KEEPConfig (keep_inference.py:9-22): vision_config is fixed by the timm call at
+ * keep_inference.py:32-40 (ViT-L/16), text_config is the BertConfig dict, projection_dim = 768. */
+typedef struct KeepB200Config {
+  int32_t struct_size; /* = sizeof(KeepB200Config), for ABI evolution */
+  /* vision tower */
+  int32_t img_size;   /* 224 */
+  int32_t patch_size; /* 16 (only 16 is supported) */
+  int32_t vit_width;  /* 1024 */
+  int32_t vit_depth;  /* 24 */
+  int32_t vit_heads;  /* 16 (head dim must be 64) */
+  int32_t vit_mlp;    /* 4096 */
+  float vit_ln_eps;   /* 1e-6 */
+  int32_t proj_dim;   /* 768 */
+  /* text tower (BertConfig) */
+  int32_t vocab_size;   /* 30522 */
+  int32_t hidden;       /* 768 */
+  int32_t layers;       /* 12 */
+  int32_t heads;        /* 12 (head dim must be 64) */
+  int32_t intermediate; /* 3072 */
+  int32_t max_pos;      /* 512 */
+  int32_t type_vocab;   /* 2 */
+  float bert_ln_eps;    /* 1e-12 */
+  /* numerics */
+  int32_t operand_dtype; /* KEEPB200_FP16 (default; ~1e-3 vs the fp32 reference) or KEEPB200_BF16 */
+} KeepB200Config;
+
+int keepb200_version(void);
+const char* keepb200_last_error(void);
+
+/* ---- model handle -------------------------------------------------------------------------------- */
+int keepb200_create(const KeepB200Config* cfg, int device, void** handle);
+void keepb200_destroy(void* handle);
+
+/* Load one tensor of the reference state-dict (names exactly as in KEEPModel.state_dict(), e.g.
+ * "visual.blocks.0.attn.qkv.weight", "text.encoder.layer.3.attention.self.query.weight", "logit_scale").
+ * `data` is a contiguous fp32 DEVICE tensor of the reference shape; it is converted/repacked into the
+ * kernel layout (16-bit K-major GEMM operands, fused BERT q|k|v) and the caller keeps ownership.
+ * Unknown names and shape mismatches are errors, as with load_state_dict(strict=True) (keep_inference.py:83). */
+int keepb200_load_weight(void* handle, const char* name, const float* data, const int64_t* shape, int ndim,
+                         void* stream);
+/* number of state-dict tensors the handle expects / name of the i-th one (host strings) */
+int keepb200_num_weights(void* handle);
+const char* keepb200_weight_name(void* handle, int index);
+/* strict check that every expected tensor was loaded; must be called before encode_* */
+int keepb200_finalize(void* handle);
+
+size_t keepb200_workspace_bytes(void* handle, int op, int64_t n, int64_t seq_len);
+
+/* out[B, proj_dim] fp32, unit L2 norm = normalize(visual_head(ViT(tiles)))  (keep_inference.py:54-58).
+ * The batch is processed in chunks as large as the workspace allows (>= 1 tile). */
+int keepb200_encode_image(void* handle, const void* tiles, int layout, int64_t B, float* out, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* out[P, hidden] fp32, unit L2 norm = normalize(BertModel(ids, type_ids, mask).pooler_output)
+ * (keep_inference.py:60-62). ids/type_ids/mask are int64 [P,S] row-major (type_ids or mask may be NULL:
+ * zeros / ones). `s_eff` (1..S) is the number of leading positions to compute: positions >= s_eff must be
+ * masked in every row, in which case the result is identical to the padded computation; pass S to disable. */
+int keepb200_encode_text(void* handle, const int64_t* ids, const int64_t* type_ids, const int64_t* mask, int64_t P,
+                         int64_t S, int64_t s_eff, float* out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ---- similarity (no handle) ------------------------------------------------------------------------ */
+/* logits[N,P] = normalize(feats)[N,D] @ cls[D,P];  probs[N,P] = softmax(temp * logits) over each
+ * consecutive group of `group` columns (0 = one group of all P columns, the reference's single
+ * classifier [D,C]; K stacked classifiers of C classes use group = C). feats and cls are fp32, cls in the
+ * reference's [D,P] layout (utils.py:83). logits or probs may be NULL (not both). D % 4 == 0. */
+int keepb200_similarity(const float* feats, int64_t N, int64_t D, const float* cls, int64_t P, int group,
+                        float temp, float* logits, float* probs, void* stream);
+
+/* Prompt screening (utils.py:107-146): for K classifiers of C classes stacked as cls[D, K*C], with
+ * logits_k = normalize(feats) @ cls_k: scores[k] = mean_n( top1 - top2 - |top1 + top2 - 1| ). */
+int keepb200_prompt_scores(const float* feats, int64_t N, int64_t D, const float* cls, int64_t K, int64_t C,
+                           float* scores, void* workspace, size_t workspace_bytes, void* stream);
+
+/* refine_seg (detection_utils.py:39-74 et al.): coords int64 [N,2] (x,y), probs fp32 [N,C].
+ * First occurrence of a coordinate wins; with overlap != 0 every kept tile's probabilities are replaced by
+ * the mean over the present tiles among (x-ps,y-ps),(x,y-ps),(x-ps,y),(x,y).
+ * keep[N] uint8 = 1 for first occurrences; refined[N,C] fp32 (rows with keep==0 are zero). */
+int keepb200_refine(const int64_t* coords, const float* probs, int64_t N, int64_t C, int64_t patch_size, int overlap,
+                    uint8_t* keep, float* refined, void* workspace, size_t workspace_bytes, void* stream);
+size_t keepb200_refine_workspace_bytes(int64_t N);
+
+/* ---- single-kernel entry points (unit tests and profiling) ------------------------------------------- */
+/* out = epilogue(A[M,K] . W[N,K]^T); epi: 0 bias->16-bit, 1 bias+GELU(erf)->16-bit,
+ * 2 resid + gamma*(acc+bias) -> fp32, 3 bias -> fp32, 4 ViT patch-embed scatter (+pos) -> fp32 */
+int keepb200_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epi, int bf16,
+                     const float* bias, const float* gamma, const float* resid, int64_t ldr, void* out, int64_t ldo,
+                     const float* pos, int patches, void* stream);
+int keepb200_op_layernorm(const float* x, int64_t row_stride, int64_t rows, int D, const float* w, const float* b,
+                          float eps, void* y16, int bf16, float* y32, void* stream);
+int keepb200_op_attention(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
+                          int64_t mask_stride, float scale, void* stream);
+int keepb200_op_act_l2norm(const float* x, int64_t rows, int D, int act, float* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KEEP_B200_H_ */

@@ -1,0 +1,575 @@
+// C ABI of libkeep_b200.so (include/keep_b200.h): model handle, strict state-dict ingestion with
+// repacking into kernel layouts, and the encode_image / encode_text / similarity / screening / refine
+// pipelines expressed as sequences of the kernels in this directory on one CUDA stream.
+#include "../../include/keep_b200.h"
+#include "common.h"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace kb;
+
+namespace {
+
+// One tensor of the reference state-dict and where it lands.
+struct WeightSlot {
+  std::string name;
+  std::vector<int64_t> shape;  // reference shape
+  bool as16 = false;           // converted to the 16-bit operand dtype (GEMM weights)
+  void* dst = nullptr;         // device destination (base of the owning allocation + offset)
+  bool loaded = false;
+  bool ignored = false;        // accepted but unused (logit_scale: dead at inference)
+};
+
+struct VitBlock {
+  float *n1w, *n1b, *qkv_b, *proj_b, *ls1, *n2w, *n2b, *fc1_b, *fc2_b, *ls2;
+  void *qkv_w, *proj_w, *fc1_w, *fc2_w;
+};
+struct BertLayer {
+  void *qkv_w, *ao_w, *in_w, *out_w;
+  float *qkv_b, *ao_b, *ao_lnw, *ao_lnb, *in_b, *out_b, *out_lnw, *out_lnb;
+};
+
+struct Model {
+  KeepB200Config cfg;
+  int device = 0;
+  bool finalized = false;
+  std::vector<WeightSlot> slots;
+  std::unordered_map<std::string, int> index;
+  std::vector<void*> allocs;
+  // vision
+  float *cls = nullptr, *pos = nullptr, *pe_b = nullptr, *norm_w = nullptr, *norm_b = nullptr;
+  void* pe_w = nullptr;
+  std::vector<VitBlock> blocks;
+  void *h0_w = nullptr, *h2_w = nullptr;
+  float *h0_b = nullptr, *h2_b = nullptr;
+  // text
+  float *word = nullptr, *tpos = nullptr, *ttype = nullptr, *emb_lnw = nullptr, *emb_lnb = nullptr;
+  std::vector<BertLayer> layers;
+  void* pool_w = nullptr;
+  float* pool_b = nullptr;
+
+  int grid() const { return cfg.img_size / cfg.patch_size; }
+  int tokens() const { return grid() * grid() + 1; }
+};
+
+int alloc_dev(Model* m, size_t bytes, void** p) {
+  KB_CUDA_CHECK(cudaMalloc(p, bytes));
+  m->allocs.push_back(*p);
+  return KB_OK;
+}
+
+// register a slot whose destination is (base + elem_offset) of an allocation of `as16 ? 2 : 4`-byte elements
+void add_slot(Model* m, const std::string& name, std::vector<int64_t> shape, bool as16, void* base, size_t elem_off) {
+  WeightSlot s;
+  s.name = name;
+  s.shape = std::move(shape);
+  s.as16 = as16;
+  s.dst = static_cast<char*>(base) + elem_off * (as16 ? 2 : 4);
+  m->index[name] = (int)m->slots.size();
+  m->slots.push_back(std::move(s));
+}
+
+#define KB_TRY(expr)            \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != KB_OK) return _rc; \
+  } while (0)
+
+int new_f32(Model* m, const std::string& name, std::vector<int64_t> shape, float** out) {
+  size_t n = 1;
+  for (auto d : shape) n *= (size_t)d;
+  void* p;
+  KB_TRY(alloc_dev(m, n * 4, &p));
+  *out = static_cast<float*>(p);
+  add_slot(m, name, std::move(shape), false, p, 0);
+  return KB_OK;
+}
+int new_w16(Model* m, const std::string& name, std::vector<int64_t> shape, void** out) {
+  size_t n = 1;
+  for (auto d : shape) n *= (size_t)d;
+  void* p;
+  KB_TRY(alloc_dev(m, n * 2, &p));
+  *out = p;
+  add_slot(m, name, std::move(shape), true, p, 0);
+  return KB_OK;
+}
+
+int build_tables(Model* m) {
+  const KeepB200Config& c = m->cfg;
+  const int D = c.vit_width, F = c.vit_mlp, T = m->tokens(), ps = c.patch_size;
+  // ---- vision tower: timm vit_large_patch16_224 state-dict ----
+  KB_TRY(new_f32(m, "visual.cls_token", {1, 1, D}, &m->cls));
+  KB_TRY(new_f32(m, "visual.pos_embed", {1, T, D}, &m->pos));
+  KB_TRY(new_w16(m, "visual.patch_embed.proj.weight", {D, 3, ps, ps}, &m->pe_w));
+  KB_TRY(new_f32(m, "visual.patch_embed.proj.bias", {D}, &m->pe_b));
+  m->blocks.resize(c.vit_depth);
+  for (int i = 0; i < c.vit_depth; ++i) {
+    VitBlock& b = m->blocks[i];
+    const std::string p = "visual.blocks." + std::to_string(i) + ".";
+    KB_TRY(new_f32(m, p + "norm1.weight", {D}, &b.n1w));
+    KB_TRY(new_f32(m, p + "norm1.bias", {D}, &b.n1b));
+    KB_TRY(new_w16(m, p + "attn.qkv.weight", {3 * D, D}, &b.qkv_w));
+    KB_TRY(new_f32(m, p + "attn.qkv.bias", {3 * D}, &b.qkv_b));
+    KB_TRY(new_w16(m, p + "attn.proj.weight", {D, D}, &b.proj_w));
+    KB_TRY(new_f32(m, p + "attn.proj.bias", {D}, &b.proj_b));
+    KB_TRY(new_f32(m, p + "ls1.gamma", {D}, &b.ls1));
+    KB_TRY(new_f32(m, p + "norm2.weight", {D}, &b.n2w));
+    KB_TRY(new_f32(m, p + "norm2.bias", {D}, &b.n2b));
+    KB_TRY(new_w16(m, p + "mlp.fc1.weight", {F, D}, &b.fc1_w));
+    KB_TRY(new_f32(m, p + "mlp.fc1.bias", {F}, &b.fc1_b));
+    KB_TRY(new_w16(m, p + "mlp.fc2.weight", {D, F}, &b.fc2_w));
+    KB_TRY(new_f32(m, p + "mlp.fc2.bias", {D}, &b.fc2_b));
+    KB_TRY(new_f32(m, p + "ls2.gamma", {D}, &b.ls2));
+  }
+  KB_TRY(new_f32(m, "visual.norm.weight", {D}, &m->norm_w));
+  KB_TRY(new_f32(m, "visual.norm.bias", {D}, &m->norm_b));
+  // ---- visual_head (keep_inference.py:42-46) ----
+  KB_TRY(new_w16(m, "visual_head.0.weight", {c.proj_dim, D}, &m->h0_w));
+  KB_TRY(new_f32(m, "visual_head.0.bias", {c.proj_dim}, &m->h0_b));
+  KB_TRY(new_w16(m, "visual_head.2.weight", {c.proj_dim, c.proj_dim}, &m->h2_w));
+  KB_TRY(new_f32(m, "visual_head.2.bias", {c.proj_dim}, &m->h2_b));
+  // ---- logit_scale (keep_inference.py:52): present in the state-dict, unused at inference ----
+  {
+    WeightSlot s;
+    s.name = "logit_scale";
+    s.ignored = true;
+    m->index[s.name] = (int)m->slots.size();
+    m->slots.push_back(s);
+  }
+  // ---- text tower: transformers BertModel state-dict ----
+  const int d = c.hidden, I = c.intermediate;
+  KB_TRY(new_f32(m, "text.embeddings.word_embeddings.weight", {c.vocab_size, d}, &m->word));
+  KB_TRY(new_f32(m, "text.embeddings.position_embeddings.weight", {c.max_pos, d}, &m->tpos));
+  KB_TRY(new_f32(m, "text.embeddings.token_type_embeddings.weight", {c.type_vocab, d}, &m->ttype));
+  KB_TRY(new_f32(m, "text.embeddings.LayerNorm.weight", {d}, &m->emb_lnw));
+  KB_TRY(new_f32(m, "text.embeddings.LayerNorm.bias", {d}, &m->emb_lnb));
+  m->layers.resize(c.layers);
+  for (int i = 0; i < c.layers; ++i) {
+    BertLayer& L = m->layers[i];
+    const std::string p = "text.encoder.layer." + std::to_string(i) + ".";
+    // query / key / value are fused into one [3d, d] operand and one [3d] bias (rows q | k | v)
+    void* qkv_w;
+    void* qkv_b;
+    KB_TRY(alloc_dev(m, (size_t)3 * d * d * 2, &qkv_w));
+    KB_TRY(alloc_dev(m, (size_t)3 * d * 4, &qkv_b));
+    L.qkv_w = qkv_w;
+    L.qkv_b = static_cast<float*>(qkv_b);
+    const char* nm[3] = {"query", "key", "value"};
+    for (int j = 0; j < 3; ++j) {
+      add_slot(m, p + "attention.self." + nm[j] + ".weight", {d, d}, true, qkv_w, (size_t)j * d * d);
+      add_slot(m, p + "attention.self." + nm[j] + ".bias", {d}, false, qkv_b, (size_t)j * d);
+    }
+    KB_TRY(new_w16(m, p + "attention.output.dense.weight", {d, d}, &L.ao_w));
+    KB_TRY(new_f32(m, p + "attention.output.dense.bias", {d}, &L.ao_b));
+    KB_TRY(new_f32(m, p + "attention.output.LayerNorm.weight", {d}, &L.ao_lnw));
+    KB_TRY(new_f32(m, p + "attention.output.LayerNorm.bias", {d}, &L.ao_lnb));
+    KB_TRY(new_w16(m, p + "intermediate.dense.weight", {I, d}, &L.in_w));
+    KB_TRY(new_f32(m, p + "intermediate.dense.bias", {I}, &L.in_b));
+    KB_TRY(new_w16(m, p + "output.dense.weight", {d, I}, &L.out_w));
+    KB_TRY(new_f32(m, p + "output.dense.bias", {d}, &L.out_b));
+    KB_TRY(new_f32(m, p + "output.LayerNorm.weight", {d}, &L.out_lnw));
+    KB_TRY(new_f32(m, p + "output.LayerNorm.bias", {d}, &L.out_lnb));
+  }
+  KB_TRY(new_w16(m, "text.pooler.dense.weight", {d, d}, &m->pool_w));
+  KB_TRY(new_f32(m, "text.pooler.dense.bias", {d}, &m->pool_b));
+  return KB_OK;
+}
+
+int validate_cfg(const KeepB200Config& c) {
+  if (c.struct_size != (int32_t)sizeof(KeepB200Config))
+    return set_error(KB_ERR_ARG, "config: struct_size %d != %zu", c.struct_size, sizeof(KeepB200Config));
+  if (c.patch_size != 16) return set_error(KB_ERR_ARG, "config: patch_size %d unsupported (16 only)", c.patch_size);
+  if (c.img_size <= 0 || c.img_size % 16 != 0) return set_error(KB_ERR_ARG, "config: img_size %d", c.img_size);
+  if (c.vit_width != c.vit_heads * 64 || c.hidden != c.heads * 64)
+    return set_error(KB_ERR_ARG, "config: head dim must be 64 (width %d / heads %d, hidden %d / heads %d)", c.vit_width,
+                     c.vit_heads, c.hidden, c.heads);
+  if (c.vit_width % 128 || c.vit_width > 1024 || c.hidden % 128 || c.hidden > 1024 || c.proj_dim % 128 ||
+      c.proj_dim > 1024)
+    return set_error(KB_ERR_ARG, "config: widths must be multiples of 128 and <= 1024");
+  if (c.vit_mlp % 64 || c.intermediate % 64) return set_error(KB_ERR_ARG, "config: mlp widths must be multiples of 64");
+  if (c.vit_depth < 1 || c.layers < 1) return set_error(KB_ERR_ARG, "config: depth/layers must be >= 1");
+  if (c.operand_dtype != KEEPB200_FP16 && c.operand_dtype != KEEPB200_BF16)
+    return set_error(KB_ERR_ARG, "config: operand_dtype %d", c.operand_dtype);
+  return KB_OK;
+}
+
+int check_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return set_error(KB_ERR_CUDA, "no CUDA device available (%s); keep_b200 has no CPU path", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return set_error(KB_ERR_ARG, "device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  KB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return set_error(KB_ERR_CUDA, "device %d is sm_%d%d; keep_b200 kernels are built for sm_100a only", device, prop.major,
+                     prop.minor);
+  return KB_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- workspace layouts -------------------------------------------------------------------------------------
+struct ImageWs {
+  size_t x, xn, qkv, att, hid, cls16, h1, feat, total;
+};
+ImageWs image_ws(const Model* m, int64_t n) {
+  const KeepB200Config& c = m->cfg;
+  const size_t M = (size_t)n * m->tokens();
+  const size_t D = c.vit_width, F = c.vit_mlp;
+  const size_t patch_bytes = (size_t)n * (m->tokens() - 1) * 768 * 2;
+  ImageWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  w.x = take(M * D * 4);
+  w.xn = take(M * D * 2);
+  w.qkv = take(M * 3 * D * 2);
+  w.att = take(M * D * 2);
+  size_t hid_bytes = M * F * 2;
+  if (patch_bytes > hid_bytes) hid_bytes = patch_bytes;  // the patch matrix aliases the MLP hidden buffer
+  w.hid = take(hid_bytes);
+  w.cls16 = take((size_t)n * D * 2);
+  w.h1 = take((size_t)n * c.proj_dim * 2);
+  w.feat = take((size_t)n * c.proj_dim * 4);
+  w.total = off;
+  return w;
+}
+struct TextWs {
+  size_t x32, x16, qkv, att, hid, pooled, total;
+};
+TextWs text_ws(const Model* m, int64_t n, int64_t s) {
+  const KeepB200Config& c = m->cfg;
+  const size_t M = (size_t)n * s, d = c.hidden, I = c.intermediate;
+  TextWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  w.x32 = take(M * d * 4);
+  w.x16 = take(M * d * 2);
+  w.qkv = take(M * 3 * d * 2);
+  w.att = take(M * d * 2);
+  w.hid = take(M * I * 2);
+  w.pooled = take((size_t)n * d * 4);
+  w.total = off;
+  return w;
+}
+
+int gemm(const void* A, int64_t lda, const void* W, int M, int N, int K, int epi, int bf16, const float* bias,
+         const float* gamma, const float* resid, void* out, int64_t ldo, cudaStream_t st, const float* pos = nullptr,
+         int patches = 0) {
+  GemmArgs a;
+  a.A = A; a.lda = lda; a.W = W; a.ldw = K; a.M = M; a.N = N; a.K = K; a.epi = epi; a.bf16 = bf16;
+  a.bias = bias; a.gamma = gamma; a.resid = resid; a.ldr = ldo; a.out = out; a.ldo = ldo; a.pos = pos;
+  a.patches = patches;
+  return launch_gemm(a, st);
+}
+
+int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, float* out, char* ws, cudaStream_t st) {
+  const KeepB200Config& c = m->cfg;
+  const int bf = c.operand_dtype, D = c.vit_width, F = c.vit_mlp, T = m->tokens(), G = m->grid();
+  const int M = (int)(n * T);
+  const ImageWs w = image_ws(m, n);
+  float* x = reinterpret_cast<float*>(ws + w.x);
+  void* xn = ws + w.xn;
+  void* qkv = ws + w.qkv;
+  void* att = ws + w.att;
+  void* hid = ws + w.hid;
+  void* cls16 = ws + w.cls16;
+  void* h1 = ws + w.h1;
+  float* feat = reinterpret_cast<float*>(ws + w.feat);
+
+  // patch gather (+ CLS rows), then patch-embed GEMM scattering into x[b, 1+p, :] with +bias +pos
+  if (layout == KEEPB200_TILES_F32_NCHW)
+    KB_TRY(launch_im2col(static_cast<const float*>(tiles), n, G, hid, bf, m->cls, m->pos, x, D, st));
+  else
+    KB_TRY(launch_im2col_u8(static_cast<const uint8_t*>(tiles), n, G, hid, bf, m->cls, m->pos, x, D, st));
+  KB_TRY(gemm(hid, 768, m->pe_w, (int)(n * (T - 1)), D, 768, EPI_PATCH_F32, bf, m->pe_b, nullptr, nullptr, x, D, st,
+              m->pos, T - 1));
+  for (int i = 0; i < c.vit_depth; ++i) {
+    const VitBlock& b = m->blocks[i];
+    KB_TRY(launch_layernorm(x, D, M, D, b.n1w, b.n1b, c.vit_ln_eps, xn, bf, nullptr, st));
+    KB_TRY(gemm(xn, D, b.qkv_w, M, 3 * D, D, EPI_BIAS_HALF, bf, b.qkv_b, nullptr, nullptr, qkv, 3 * D, st));
+    KB_TRY(launch_attention(qkv, att, (int)n, T, c.vit_heads, bf, nullptr, 0, 0.125f, st));
+    KB_TRY(gemm(att, D, b.proj_w, M, D, D, EPI_RESID_F32, bf, b.proj_b, b.ls1, x, x, D, st));
+    KB_TRY(launch_layernorm(x, D, M, D, b.n2w, b.n2b, c.vit_ln_eps, xn, bf, nullptr, st));
+    KB_TRY(gemm(xn, D, b.fc1_w, M, F, D, EPI_BIAS_GELU_HALF, bf, b.fc1_b, nullptr, nullptr, hid, F, st));
+    KB_TRY(gemm(hid, F, b.fc2_w, M, D, F, EPI_RESID_F32, bf, b.fc2_b, b.ls2, x, x, D, st));
+  }
+  // final norm on the CLS rows only (global_pool='token'), visual_head, L2-normalise
+  KB_TRY(launch_layernorm(x, (int64_t)T * D, n, D, m->norm_w, m->norm_b, c.vit_ln_eps, cls16, bf, nullptr, st));
+  KB_TRY(gemm(cls16, D, m->h0_w, (int)n, c.proj_dim, D, EPI_BIAS_GELU_HALF, bf, m->h0_b, nullptr, nullptr, h1, c.proj_dim,
+              st));
+  KB_TRY(gemm(h1, c.proj_dim, m->h2_w, (int)n, c.proj_dim, c.proj_dim, EPI_BIAS_F32, bf, m->h2_b, nullptr, nullptr, feat,
+              c.proj_dim, st));
+  KB_TRY(launch_act_l2norm(feat, n, c.proj_dim, 0, out, st));
+  return KB_OK;
+}
+
+int encode_text_chunk(Model* m, const int64_t* ids, const int64_t* tts, const int64_t* mask, int64_t n, int64_t S,
+                      int64_t se, float* out, char* ws, cudaStream_t st) {
+  const KeepB200Config& c = m->cfg;
+  const int bf = c.operand_dtype, d = c.hidden, I = c.intermediate;
+  const int M = (int)(n * se);
+  const TextWs w = text_ws(m, n, se);
+  float* x32 = reinterpret_cast<float*>(ws + w.x32);
+  void* x16 = ws + w.x16;
+  void* qkv = ws + w.qkv;
+  void* att = ws + w.att;
+  void* hid = ws + w.hid;
+  float* pooled = reinterpret_cast<float*>(ws + w.pooled);
+  KB_TRY(launch_bert_embed(ids, tts, S, n, (int)se, d, m->word, m->ttype, m->tpos, m->emb_lnw, m->emb_lnb,
+                           c.bert_ln_eps, x32, x16, bf, c.vocab_size, c.type_vocab, st));
+  for (int i = 0; i < c.layers; ++i) {
+    const BertLayer& L = m->layers[i];
+    KB_TRY(gemm(x16, d, L.qkv_w, M, 3 * d, d, EPI_BIAS_HALF, bf, L.qkv_b, nullptr, nullptr, qkv, 3 * d, st));
+    KB_TRY(launch_attention(qkv, att, (int)n, (int)se, c.heads, bf, mask, S, 0.125f, st));
+    // post-LN: x = LN(x + dense(ctx)) ; x = LN(x + dense(gelu(dense(x))))
+    KB_TRY(gemm(att, d, L.ao_w, M, d, d, EPI_RESID_F32, bf, L.ao_b, nullptr, x32, x32, d, st));
+    KB_TRY(launch_layernorm(x32, d, M, d, L.ao_lnw, L.ao_lnb, c.bert_ln_eps, x16, bf, x32, st));
+    KB_TRY(gemm(x16, d, L.in_w, M, I, d, EPI_BIAS_GELU_HALF, bf, L.in_b, nullptr, nullptr, hid, I, st));
+    KB_TRY(gemm(hid, I, L.out_w, M, d, I, EPI_RESID_F32, bf, L.out_b, nullptr, x32, x32, d, st));
+    KB_TRY(launch_layernorm(x32, d, M, d, L.out_lnw, L.out_lnb, c.bert_ln_eps, x16, bf, x32, st));
+  }
+  // pooler on the [CLS] rows (row pitch se*d), tanh, L2-normalise
+  KB_TRY(gemm(x16, (int64_t)se * d, m->pool_w, (int)n, d, d, EPI_BIAS_F32, bf, m->pool_b, nullptr, nullptr, pooled, d, st));
+  KB_TRY(launch_act_l2norm(pooled, n, d, 1, out, st));
+  return KB_OK;
+}
+
+}  // namespace
+
+// =============================================================================================================
+// exported C ABI
+// =============================================================================================================
+extern "C" {
+
+int keepb200_version(void) { return KEEPB200_ABI_VERSION; }
+const char* keepb200_last_error(void) { return last_error(); }
+
+int keepb200_create(const KeepB200Config* cfg, int device, void** handle) {
+  if (!cfg || !handle) return set_error(KB_ERR_ARG, "create: null argument");
+  *handle = nullptr;
+  KB_TRY(validate_cfg(*cfg));
+  KB_TRY(check_device(device));
+  KB_CUDA_CHECK(cudaSetDevice(device));
+  Model* m = new Model();
+  m->cfg = *cfg;
+  m->device = device;
+  int rc = build_tables(m);
+  if (rc != KB_OK) {
+    for (void* p : m->allocs) cudaFree(p);
+    delete m;
+    return rc;
+  }
+  *handle = m;
+  return KB_OK;
+}
+
+void keepb200_destroy(void* handle) {
+  if (!handle) return;
+  Model* m = static_cast<Model*>(handle);
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+}
+
+int keepb200_num_weights(void* handle) {
+  if (!handle) return set_error(KB_ERR_ARG, "null handle");
+  return (int)static_cast<Model*>(handle)->slots.size();
+}
+const char* keepb200_weight_name(void* handle, int index) {
+  if (!handle) return nullptr;
+  Model* m = static_cast<Model*>(handle);
+  if (index < 0 || index >= (int)m->slots.size()) return nullptr;
+  return m->slots[index].name.c_str();
+}
+
+int keepb200_load_weight(void* handle, const char* name, const float* data, const int64_t* shape, int ndim,
+                         void* stream) {
+  if (!handle || !name) return set_error(KB_ERR_ARG, "load_weight: null argument");
+  Model* m = static_cast<Model*>(handle);
+  auto it = m->index.find(name);
+  if (it == m->index.end()) {
+    // buffers some transformers versions serialise; not parameters
+    if (std::strcmp(name, "text.embeddings.position_ids") == 0 || std::strcmp(name, "text.embeddings.token_type_ids") == 0)
+      return KB_OK;
+    return set_error(KB_ERR_ARG, "load_weight: unexpected key \"%s\"", name);
+  }
+  WeightSlot& s = m->slots[it->second];
+  if (s.ignored) {
+    s.loaded = true;
+    return KB_OK;
+  }
+  if (!data) return set_error(KB_ERR_ARG, "load_weight: null data for \"%s\"", name);
+  bool same = (ndim == (int)s.shape.size());
+  for (int i = 0; same && i < ndim; ++i) same = (shape[i] == s.shape[i]);
+  if (!same) {
+    std::string want, got;
+    for (auto d : s.shape) want += std::to_string(d) + ",";
+    for (int i = 0; i < ndim; ++i) got += std::to_string(shape[i]) + ",";
+    return set_error(KB_ERR_ARG, "load_weight: size mismatch for \"%s\": expected [%s] got [%s]", name, want.c_str(),
+                     got.c_str());
+  }
+  size_t n = 1;
+  for (auto d : s.shape) n *= (size_t)d;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (s.as16)
+    KB_TRY(launch_cast_f32_to_16(data, s.dst, (int64_t)n, m->cfg.operand_dtype, st));
+  else
+    KB_CUDA_CHECK(cudaMemcpyAsync(s.dst, data, n * 4, cudaMemcpyDeviceToDevice, st));
+  s.loaded = true;
+  m->finalized = false;
+  return KB_OK;
+}
+
+int keepb200_finalize(void* handle) {
+  if (!handle) return set_error(KB_ERR_ARG, "null handle");
+  Model* m = static_cast<Model*>(handle);
+  std::string missing;
+  int count = 0;
+  for (const WeightSlot& s : m->slots)
+    if (!s.loaded) {
+      if (count < 4) missing += "\"" + s.name + "\" ";
+      ++count;
+    }
+  if (count) return set_error(KB_ERR_STATE, "finalize: %d missing key(s): %s%s", count, missing.c_str(), count > 4 ? "..." : "");
+  m->finalized = true;
+  return KB_OK;
+}
+
+size_t keepb200_workspace_bytes(void* handle, int op, int64_t n, int64_t seq_len) {
+  if (!handle || n <= 0) return 0;
+  Model* m = static_cast<Model*>(handle);
+  if (op == KEEPB200_OP_ENCODE_IMAGE) return image_ws(m, n).total;
+  if (op == KEEPB200_OP_ENCODE_TEXT) return text_ws(m, n, seq_len > 0 ? seq_len : m->cfg.max_pos).total;
+  return 0;
+}
+
+int keepb200_encode_image(void* handle, const void* tiles, int layout, int64_t B, float* out, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (!handle) return set_error(KB_ERR_ARG, "null handle");
+  Model* m = static_cast<Model*>(handle);
+  if (!m->finalized) return set_error(KB_ERR_STATE, "encode_image: handle not finalised");
+  if (B == 0) return KB_OK;
+  if (B < 0 || !tiles || !out) return set_error(KB_ERR_ARG, "encode_image: bad arguments");
+  if (layout != KEEPB200_TILES_F32_NCHW && layout != KEEPB200_TILES_U8_NHWC)
+    return set_error(KB_ERR_ARG, "encode_image: unknown tile layout %d", layout);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return set_error(KB_ERR_ARG, "encode_image: workspace must be 1024-byte aligned");
+  const size_t per1 = image_ws(m, 1).total;
+  if (!workspace || workspace_bytes < per1)
+    return set_error(KB_ERR_WORKSPACE, "encode_image: workspace %zu B < %zu B needed for one tile", workspace_bytes, per1);
+  // largest chunk that fits (the layout is monotone in n); rows are limited to int32 GEMM extents
+  int64_t chunk = B;
+  const int64_t max_rows = (int64_t)1 << 30;
+  if (chunk * m->tokens() > max_rows) chunk = max_rows / m->tokens();
+  while (chunk > 1 && image_ws(m, chunk).total > workspace_bytes) {
+    int64_t guess = (int64_t)(workspace_bytes / (image_ws(m, chunk).total / (double)chunk));
+    chunk = guess < chunk ? (guess > 1 ? guess : 1) : chunk - 1;
+  }
+  const size_t tile_elems = (size_t)3 * m->cfg.img_size * m->cfg.img_size;
+  const size_t tile_bytes = tile_elems * (layout == KEEPB200_TILES_F32_NCHW ? 4 : 1);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+    const int64_t n = (B - b0 < chunk) ? (B - b0) : chunk;
+    KB_TRY(encode_image_chunk(m, static_cast<const char*>(tiles) + (size_t)b0 * tile_bytes, layout, n,
+                              out + (size_t)b0 * m->cfg.proj_dim, static_cast<char*>(workspace), st));
+  }
+  return KB_OK;
+}
+
+int keepb200_encode_text(void* handle, const int64_t* ids, const int64_t* type_ids, const int64_t* mask, int64_t P,
+                         int64_t S, int64_t s_eff, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!handle) return set_error(KB_ERR_ARG, "null handle");
+  Model* m = static_cast<Model*>(handle);
+  if (!m->finalized) return set_error(KB_ERR_STATE, "encode_text: handle not finalised");
+  if (P == 0) return KB_OK;
+  if (P < 0 || !ids || !out) return set_error(KB_ERR_ARG, "encode_text: bad arguments");
+  if (S < 1 || S > m->cfg.max_pos || S > 512)
+    return set_error(KB_ERR_ARG, "encode_text: sequence length %lld outside [1, %d]", (long long)S,
+                     m->cfg.max_pos < 512 ? m->cfg.max_pos : 512);
+  if (s_eff < 1 || s_eff > S) return set_error(KB_ERR_ARG, "encode_text: s_eff %lld outside [1, %lld]", (long long)s_eff, (long long)S);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return set_error(KB_ERR_ARG, "encode_text: workspace must be 1024-byte aligned");
+  const size_t per1 = text_ws(m, 1, s_eff).total;
+  if (!workspace || workspace_bytes < per1)
+    return set_error(KB_ERR_WORKSPACE, "encode_text: workspace %zu B < %zu B needed for one prompt", workspace_bytes, per1);
+  int64_t chunk = P;
+  const int64_t max_rows = (int64_t)1 << 30;
+  if (chunk * s_eff > max_rows) chunk = max_rows / s_eff;
+  while (chunk > 1 && text_ws(m, chunk, s_eff).total > workspace_bytes) {
+    int64_t guess = (int64_t)(workspace_bytes / (text_ws(m, chunk, s_eff).total / (double)chunk));
+    chunk = guess < chunk ? (guess > 1 ? guess : 1) : chunk - 1;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int64_t p0 = 0; p0 < P; p0 += chunk) {
+    const int64_t n = (P - p0 < chunk) ? (P - p0) : chunk;
+    KB_TRY(encode_text_chunk(m, ids + p0 * S, type_ids ? type_ids + p0 * S : nullptr, mask ? mask + p0 * S : nullptr, n, S,
+                             s_eff, out + (size_t)p0 * m->cfg.hidden, static_cast<char*>(workspace), st));
+  }
+  return KB_OK;
+}
+
+int keepb200_similarity(const float* feats, int64_t N, int64_t D, const float* cls, int64_t P, int group, float temp,
+                        float* logits, float* probs, void* stream) {
+  if (N == 0 || P == 0) return KB_OK;
+  if (!feats || !cls || N < 0 || P < 0 || D <= 0) return set_error(KB_ERR_ARG, "similarity: bad arguments");
+  if (P > (1 << 30)) return set_error(KB_ERR_ARG, "similarity: P too large");
+  return launch_similarity(feats, N, (int)D, cls, (int)P, group, temp, logits, probs, static_cast<cudaStream_t>(stream));
+}
+
+int keepb200_prompt_scores(const float* feats, int64_t N, int64_t D, const float* cls, int64_t K, int64_t C,
+                           float* scores, void* workspace, size_t workspace_bytes, void* stream) {
+  if (K == 0) return KB_OK;
+  if (!feats || !cls || !scores || N <= 0 || K < 0 || C < 2 || D <= 0) return set_error(KB_ERR_ARG, "prompt_scores: bad arguments");
+  const int64_t P = K * C;
+  const size_t row_bytes = (size_t)P * 4;
+  if (!workspace || workspace_bytes < row_bytes * 64)
+    return set_error(KB_ERR_WORKSPACE, "prompt_scores: workspace %zu B < %zu B (64 rows of logits)", workspace_bytes, row_bytes * 64);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KB_CUDA_CHECK(cudaMemsetAsync(scores, 0, (size_t)K * 4, st));
+  int64_t chunk = (int64_t)(workspace_bytes / row_bytes);
+  chunk = chunk / 64 * 64;
+  if (chunk > N) chunk = N;
+  float* logits = static_cast<float*>(workspace);
+  for (int64_t r0 = 0; r0 < N; r0 += chunk) {
+    const int64_t n = (N - r0 < chunk) ? (N - r0) : chunk;
+    KB_TRY(launch_similarity(feats + r0 * D, n, (int)D, cls, (int)P, (int)C, 1.0f, logits, nullptr, st));
+    KB_TRY(launch_prompt_score_accum(logits, n, (int)K, (int)C, scores, st));
+  }
+  return launch_scale(scores, K, 1.0f / (float)N, st);
+}
+
+size_t keepb200_refine_workspace_bytes(int64_t N) { return N > 0 ? refine_workspace_bytes(N) : 0; }
+
+int keepb200_refine(const int64_t* coords, const float* probs, int64_t N, int64_t C, int64_t patch_size, int overlap,
+                    uint8_t* keep, float* refined, void* workspace, size_t workspace_bytes, void* stream) {
+  if (N == 0) return KB_OK;
+  if (!coords || !probs || !keep || !refined || N < 0 || C <= 0) return set_error(KB_ERR_ARG, "refine: bad arguments");
+  return launch_refine(coords, probs, N, (int)C, patch_size, overlap, keep, refined, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+// ---- single-kernel entry points -----------------------------------------------------------------------------------
+int keepb200_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epi, int bf16,
+                     const float* bias, const float* gamma, const float* resid, int64_t ldr, void* out, int64_t ldo,
+                     const float* pos, int patches, void* stream) {
+  GemmArgs a;
+  a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.M = M; a.N = N; a.K = K; a.epi = epi; a.bf16 = bf16;
+  a.bias = bias; a.gamma = gamma; a.resid = resid; a.ldr = ldr; a.out = out; a.ldo = ldo; a.pos = pos;
+  a.patches = patches;
+  return launch_gemm(a, static_cast<cudaStream_t>(stream));
+}
+int keepb200_op_layernorm(const float* x, int64_t row_stride, int64_t rows, int D, const float* w, const float* b,
+                          float eps, void* y16, int bf16, float* y32, void* stream) {
+  return launch_layernorm(x, row_stride, rows, D, w, b, eps, y16, bf16, y32, static_cast<cudaStream_t>(stream));
+}
+int keepb200_op_attention(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
+                          int64_t mask_stride, float scale, void* stream) {
+  return launch_attention(qkv, out, B, S, H, bf16, key_mask, mask_stride, scale, static_cast<cudaStream_t>(stream));
+}
+int keepb200_op_act_l2norm(const float* x, int64_t rows, int D, int act, float* y, void* stream) {
+  return launch_act_l2norm(x, rows, D, act, y, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// Host-side shared declarations for the library (error handling, tensor-map cache, kernel launchers).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace kb {
+
+// ---- error plumbing: every launcher returns 0 or a negative code and records a message ----------
+enum : int {
+  KB_OK = 0,
+  KB_ERR_ARG = -1,      // bad argument / unsupported shape
+  KB_ERR_CUDA = -2,     // CUDA runtime / driver error
+  KB_ERR_STATE = -3,    // handle not finalised, missing weight, ...
+  KB_ERR_WORKSPACE = -4 // workspace too small
+};
+int set_error(int code, const char* fmt, ...);
+const char* last_error();
+#define KB_CUDA_CHECK(expr)                                                                    \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return ::kb::set_error(::kb::KB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                \
+                             cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+  } while (0)
+
+int num_sms();
+
+// ---- TMA tensor maps ---------------------------------------------------------------------------
+// 2-D row-major matrix [rows, cols] of 2- or 4-byte elements with row pitch `ld` elements, box =
+// [box_rows, 128 bytes] and SWIZZLE_128B. Cached by value of all arguments.
+enum : int { KB_F16 = 0, KB_BF16 = 1, KB_F32 = 2 };
+int get_tmap_2d(const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                CUtensorMap* out);
+
+// ---- GEMM: out = epilogue(A[M,K] . W[N,K]^T) ------------------------------------------------------
+enum : int {
+  EPI_BIAS_HALF = 0,       // out16[r,c] = acc + bias[c]
+  EPI_BIAS_GELU_HALF = 1,  // out16[r,c] = gelu_erf(acc + bias[c])
+  EPI_RESID_F32 = 2,       // out32[r,c] = resid[r,c] + gamma[c] * (acc + bias[c])   (gamma may be null => 1)
+  EPI_BIAS_F32 = 3,        // out32[r,c] = acc + bias[c]
+  EPI_PATCH_F32 = 4        // out32[(r/P)*(P+1)+1+r%P, c] = acc + bias[c] + pos[1+r%P, c]   (ViT patch embed)
+};
+struct GemmArgs {
+  const void* A;  int64_t lda;   // [M,K] 16-bit, K contiguous
+  const void* W;  int64_t ldw;   // [N,K] 16-bit, K contiguous (torch Linear weight)
+  int M, N, K;
+  int epi;
+  int bf16;                      // 0: fp16 operands/outputs, 1: bf16
+  const float* bias;             // [N] or null
+  const float* gamma;            // [N] or null
+  const float* resid; int64_t ldr;
+  void* out; int64_t ldo;
+  const float* pos; int patches; // EPI_PATCH_F32 only
+};
+int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+
+// ---- row kernels ------------------------------------------------------------------------------------
+// y16[i,:] (and optionally y32[i,:]) = LayerNorm(x[i*row_stride : +D]) * w + b
+int launch_layernorm(const float* x, int64_t x_row_stride, int64_t rows, int D, const float* w, const float* b,
+                     float eps, void* y16, int bf16, float* y32, cudaStream_t stream);
+// act: 0 none, 1 tanh ; then y = x / max(||x||, 1e-12)
+int launch_act_l2norm(const float* x, int64_t rows, int D, int act, float* y, cudaStream_t stream);
+
+// ---- attention ----------------------------------------------------------------------------------------
+// qkv: [B*S, 3*H*64] 16-bit (q | k | v, head-major 64-wide groups); out: [B*S, H*64]
+// key_mask: optional int64 [B, mask_stride] (non-zero = attend, 0 = masked key), as BERT's attention_mask
+int launch_attention(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
+                     int64_t mask_stride, float scale, cudaStream_t stream);
+
+// ---- ViT front end ----------------------------------------------------------------------------------------
+// tiles fp32 NCHW [B,3,G*16,G*16] -> patches16 [B*G*G, 768] (col = c*256+ky*16+kx); also writes the CLS
+// rows x[b*(G*G+1), :] = cls + pos[0].
+int launch_im2col(const float* tiles, int64_t B, int G, void* patches16, int bf16, const float* cls,
+                  const float* pos, float* x, int D, cudaStream_t stream);
+// uint8 NHWC tiles [B,H,W,3] with fused (x/255-mean)/std
+int launch_im2col_u8(const uint8_t* tiles, int64_t B, int G, void* patches16, int bf16, const float* cls,
+                     const float* pos, float* x, int D, cudaStream_t stream);
+
+// ---- BERT front end ------------------------------------------------------------------------------------------
+// x32/x16[p*S+s,:] = LN(word[ids] + type[tt] + pos[s])
+int launch_bert_embed(const int64_t* ids, const int64_t* tts, int64_t id_stride, int64_t P, int S, int D,
+                      const float* word, const float* type, const float* pos, const float* lnw, const float* lnb,
+                      float eps, float* x32, void* x16, int bf16, int vocab, int type_vocab, cudaStream_t stream);
+
+// ---- similarity -------------------------------------------------------------------------------------------------
+// logits[n,p] = <feats[n,:]/max(||feats[n]||,1e-12), cls[:,p]> ; probs = softmax over each consecutive
+// group of `group` columns of (temp * logits). feats fp32 [N,D], cls fp32 [D,P] (torch layout, utils.py:83).
+int launch_similarity(const float* feats, int64_t N, int D, const float* cls, int P, int group, float temp,
+                      float* logits, float* probs, cudaStream_t stream);
+// scores[k] += sum_n(top1 - top2 - |top1 + top2 - 1|) over logits[n, k*C:(k+1)*C]  (scale by 1/N afterwards)
+int launch_prompt_score_accum(const float* logits, int64_t rows, int K, int C, float* scores, cudaStream_t stream);
+int launch_scale(float* v, int64_t n, float s, cudaStream_t stream);
+
+// ---- refine_seg ------------------------------------------------------------------------------------------------
+size_t refine_workspace_bytes(int64_t N);
+int launch_refine(const int64_t* coords, const float* probs, int64_t N, int C, int64_t ps, int overlap, uint8_t* keep,
+                  float* refined, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// generic helpers
+int launch_cast_f32_to_16(const float* src, void* dst, int64_t n, int bf16, cudaStream_t stream);
+int launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t stream);  // dst[c,r]=src[r,c]
+
+}  // namespace kb

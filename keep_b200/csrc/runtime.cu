@@ -1,0 +1,118 @@
+// Host runtime shared by the launchers: error slot, SM count, TMA tensor-map cache.
+#include "common.h"
+#include "ptx.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+namespace kb {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+const char* last_error() { return g_err; }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tensor maps
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    // resolved through the runtime so the library has no link-time dependency on libcuda
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  int64_t rows, cols, ld;
+  int dtype, box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && dtype == o.dtype &&
+           box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ static_cast<size_t>(k.rows);
+    h = h * 1000003u ^ static_cast<size_t>(k.cols);
+    h = h * 1000003u ^ static_cast<size_t>(k.ld);
+    h = h * 1000003u ^ static_cast<size_t>(k.dtype * 1024 + k.box_rows);
+    return h;
+  }
+};
+
+int get_tmap_2d(const void* ptr, int dtype, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{ptr, rows, cols, ld, dtype, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return KB_OK;
+    }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(KB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const int esz = (dtype == KB_F32) ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * esz) % 16 != 0)
+    return set_error(KB_ERR_ARG, "tensor map: base %p / pitch %lld B not 16-byte aligned", ptr, (long long)(ld * esz));
+  if (box_rows < 1 || box_rows > 256) return set_error(KB_ERR_ARG, "tensor map: box_rows=%d out of range", box_rows);
+  CUtensorMapDataType dt = dtype == KB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                           : dtype == KB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                              : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld * esz)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(KB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] ld=%lld box_rows=%d", (int)r,
+                     (long long)rows, (long long)cols, (long long)ld, box_rows);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, m);
+  }
+  *out = m;
+  return KB_OK;
+}
+
+}  // namespace kb

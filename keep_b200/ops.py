@@ -1,0 +1,151 @@
+"""Torch-tensor front ends of the handle-free C-ABI entry points (keepb200_op_*, keepb200_similarity,
+keepb200_prompt_scores, keepb200_refine).  Tensors must live on a CUDA device; nothing here computes on the
+host — arguments are validated, output tensors are allocated, and the library is called on the current stream.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+EPI_BIAS_HALF, EPI_BIAS_GELU_HALF, EPI_RESID_F32, EPI_BIAS_F32, EPI_PATCH_F32 = range(5)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.KeepB200Error("keep_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+def _is_bf16(t) -> int:
+    if t.dtype == torch.bfloat16:
+        return 1
+    if t.dtype == torch.float16:
+        return 0
+    raise TypeError(f"16-bit operand expected, got {t.dtype}")
+
+
+def gemm(a, w, epi, bias=None, gamma=None, resid=None, out=None, pos=None, patches=0):
+    """out = epilogue(a[M,K] @ w[N,K].T); a/w fp16 or bf16 (a may have a row pitch > K)."""
+    _need_cuda(a, w, bias, gamma, resid, out, pos)
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    bf = _is_bf16(a)
+    assert _is_bf16(w) == bf
+    if out is None:
+        if epi in (EPI_BIAS_HALF, EPI_BIAS_GELU_HALF):
+            out = torch.empty(M, N, dtype=a.dtype, device=a.device)
+        elif epi == EPI_PATCH_F32:
+            out = torch.zeros((M // patches) * (patches + 1), N, dtype=torch.float32, device=a.device)
+        else:
+            out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    L = _lib.lib()
+    _lib.check(
+        L.keepb200_op_gemm(
+            a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, epi, bf,
+            _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(resid), resid.stride(0) if resid is not None else 0,
+            out.data_ptr(), out.stride(0), _lib.ptr(pos), patches, _lib.stream_ptr(a.device),
+        ),
+        "op_gemm",
+    )
+    return out
+
+
+def layernorm(x, w, b, eps, out_dtype=torch.float16, want_f32=False, rows=None, row_stride=None):
+    _need_cuda(x, w, b)
+    D = w.numel()
+    if rows is None:
+        rows = x.numel() // D
+        row_stride = D
+    y16 = torch.empty(rows, D, dtype=out_dtype, device=x.device) if out_dtype is not None else None
+    y32 = torch.empty(rows, D, dtype=torch.float32, device=x.device) if want_f32 else None
+    L = _lib.lib()
+    _lib.check(
+        L.keepb200_op_layernorm(
+            x.data_ptr(), row_stride, rows, D, w.data_ptr(), b.data_ptr(), eps, _lib.ptr(y16),
+            1 if out_dtype == torch.bfloat16 else 0, _lib.ptr(y32), _lib.stream_ptr(x.device),
+        ),
+        "op_layernorm",
+    )
+    return y16, y32
+
+
+def attention(qkv, B, S, H, key_mask=None, scale=0.125):
+    """qkv [B*S, 3*H*64] 16-bit -> context [B*S, H*64]."""
+    _need_cuda(qkv, key_mask)
+    out = torch.empty(B * S, H * 64, dtype=qkv.dtype, device=qkv.device)
+    L = _lib.lib()
+    _lib.check(
+        L.keepb200_op_attention(
+            qkv.data_ptr(), out.data_ptr(), B, S, H, _is_bf16(qkv), _lib.ptr(key_mask),
+            key_mask.stride(0) if key_mask is not None else 0, scale, _lib.stream_ptr(qkv.device),
+        ),
+        "op_attention",
+    )
+    return out
+
+
+def act_l2norm(x, act=0):
+    _need_cuda(x)
+    y = torch.empty_like(x)
+    L = _lib.lib()
+    _lib.check(L.keepb200_op_act_l2norm(x.data_ptr(), x.shape[0], x.shape[1], act, y.data_ptr(), _lib.stream_ptr(x.device)), "op_act_l2norm")
+    return y
+
+
+def similarity(feats, cls, group=0, temp=10.0, want_probs=True):
+    """logits = normalize(feats) @ cls ; probs = softmax(temp*logits) per `group` columns (0 = all)."""
+    _need_cuda(feats, cls)
+    feats = feats.contiguous().float()
+    cls = cls.contiguous().float()
+    N, D = feats.shape
+    P = cls.shape[1]
+    assert cls.shape[0] == D
+    logits = torch.empty(N, P, dtype=torch.float32, device=feats.device)
+    probs = torch.empty(N, P, dtype=torch.float32, device=feats.device) if want_probs else None
+    L = _lib.lib()
+    _lib.check(
+        L.keepb200_similarity(feats.data_ptr(), N, D, cls.data_ptr(), P, group, temp, logits.data_ptr(), _lib.ptr(probs),
+                              _lib.stream_ptr(feats.device)),
+        "similarity",
+    )
+    return logits, probs
+
+
+def prompt_scores(feats, cls, K, C, workspace_mb=256):
+    """scores[k] = mean_n(top1 - top2 - |top1 + top2 - 1|) of normalize(feats) @ cls[:, k*C:(k+1)*C]."""
+    _need_cuda(feats, cls)
+    feats = feats.contiguous().float()
+    cls = cls.contiguous().float()
+    N, D = feats.shape
+    assert cls.shape == (D, K * C)
+    scores = torch.empty(K, dtype=torch.float32, device=feats.device)
+    ws_bytes = max(64 * K * C * 4, min(workspace_mb << 20, ((N + 63) // 64) * 64 * K * C * 4))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device)
+    L = _lib.lib()
+    _lib.check(
+        L.keepb200_prompt_scores(feats.data_ptr(), N, D, cls.data_ptr(), K, C, scores.data_ptr(), ws.data_ptr(), ws_bytes,
+                                 _lib.stream_ptr(feats.device)),
+        "prompt_scores",
+    )
+    return scores
+
+
+def refine(coords, probs, patch_size, overlap):
+    """Device refine_seg: returns (keep uint8 [N], refined fp32 [N,C])."""
+    _need_cuda(coords, probs)
+    coords = coords.contiguous().long()
+    probs = probs.contiguous().float()
+    N, Cc = probs.shape
+    keep = torch.empty(N, dtype=torch.uint8, device=probs.device)
+    refined = torch.empty(N, Cc, dtype=torch.float32, device=probs.device)
+    L = _lib.lib()
+    ws_bytes = L.keepb200_refine_workspace_bytes(N)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=probs.device)
+    _lib.check(
+        L.keepb200_refine(coords.data_ptr(), probs.data_ptr(), N, Cc, patch_size, 1 if overlap else 0, keep.data_ptr(),
+                          refined.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(probs.device)),
+        "refine",
+    )
+    return keep, refined
