@@ -154,7 +154,7 @@ def _create_model(name, pretrained=False, img_size=224, patch_size=16, init_valu
 
 def install_timm_shim():
     """Make `import timm; timm.create_model(...)` resolve to the restatement (timm is not installed here)."""
-    if "timm" in sys.modules and not getattr(sys.modules["timm"], "_keep_oracle_shim", False):
+    if "timm" in sys.modules:  # a real timm, or the shim installed earlier (module identity must be stable)
         return sys.modules["timm"]
     mod = types.ModuleType("timm")
     mod.create_model = _create_model

@@ -1,0 +1,217 @@
+"""GPU: every kernel behind the C ABI against a plain PyTorch fp32 statement of the same op.
+16-bit-operand kernels are compared on the same (already rounded) inputs, so the tolerance only covers the
+output rounding; fp32-output kernels are held to fp32 round-off."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _fp32_reference_math():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _rel(got, ref):
+    return ((got.float() - ref.float()).abs().max() / ref.float().abs().max()).item()
+
+
+def _gemm_inputs(M, N, K, dtype, ints=False, seed=0):
+    g = torch.Generator().manual_seed(seed + M + 3 * N + 7 * K)
+    if ints:
+        a = torch.randint(-2, 3, (M, K), generator=g).to(dtype)
+        w = torch.randint(-2, 3, (N, K), generator=g).to(dtype)
+    else:
+        a = (torch.randn(M, K, generator=g) * 0.5).to(dtype)
+        w = (torch.randn(N, K, generator=g) * 0.05).to(dtype)
+    bias = torch.randn(N, generator=g) * 0.1
+    gamma = torch.rand(N, generator=g) + 0.5
+    return a.to(DEV), w.to(DEV), bias.to(DEV), gamma.to(DEV), g
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (256, 256, 128), (1, 128, 64), (129, 768, 768)])
+def test_gemm_exact_on_integer_operands(M, N, K):
+    """Small-integer operands make every product and sum exact: any mismatch is a layout/descriptor bug."""
+    from keep_b200 import ops
+
+    a, w, bias, _, _ = _gemm_inputs(M, N, K, torch.float16, ints=True)
+    bias = bias.round()
+    out = ops.gemm(a, w, ops.EPI_BIAS_F32, bias=bias)
+    assert torch.equal(out, a.float() @ w.float().T + bias)
+
+
+@pytest.mark.parametrize("M,N,K", [(197 * 3, 768, 1024), (128 * 160, 1024, 1024), (197 * 64, 3072, 1024), (50, 2304, 768)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_gemm_bias_16bit(M, N, K, dtype):
+    from keep_b200 import ops
+
+    a, w, bias, _, _ = _gemm_inputs(M, N, K, dtype)
+    out = ops.gemm(a, w, ops.EPI_BIAS_HALF, bias=bias)
+    ref = a.float() @ w.float().T + bias
+    assert out.dtype == dtype
+    assert _rel(out, ref) < (1e-3 if dtype == torch.float16 else 8e-3)
+
+
+def test_gemm_gelu_is_exact_erf():
+    from keep_b200 import ops
+
+    a, w, bias, _, _ = _gemm_inputs(197 * 16, 4096, 1024, torch.float16)
+    out = ops.gemm(a, w, ops.EPI_BIAS_GELU_HALF, bias=bias)
+    pre = a.float() @ w.float().T + bias
+    assert _rel(out, F.gelu(pre)) < 1e-3
+    assert _rel(out, F.gelu(pre, approximate="tanh")) > _rel(out, F.gelu(pre))
+
+
+def test_gemm_residual_layerscale_in_place():
+    from keep_b200 import ops
+
+    M, N, K = 197 * 16, 1024, 4096
+    a, w, bias, gamma, g = _gemm_inputs(M, N, K, torch.float16)
+    resid = torch.randn(M, N, generator=g).to(DEV)
+    ref = resid + gamma * (a.float() @ w.float().T + bias)
+    x = resid.clone()
+    ops.gemm(a, w, ops.EPI_RESID_F32, bias=bias, gamma=gamma, resid=x, out=x)
+    assert _rel(x, ref) < 1e-5
+    y = ops.gemm(a, w, ops.EPI_RESID_F32, bias=bias, gamma=None, resid=resid)  # BERT form: no LayerScale
+    assert _rel(y, resid + a.float() @ w.float().T + bias) < 1e-5
+
+
+def test_gemm_patch_embed_scatter():
+    from keep_b200 import ops
+
+    P, B, N = 196, 5, 1024
+    a, w, bias, _, g = _gemm_inputs(P * B, N, 768, torch.float16)
+    pos = torch.randn(P + 1, N, generator=g).to(DEV)
+    out = ops.gemm(a, w, ops.EPI_PATCH_F32, bias=bias, pos=pos, patches=P)
+    ref = torch.zeros(B, P + 1, N, device=DEV)
+    ref[:, 1:] = (a.float() @ w.float().T + bias).view(B, P, N) + pos[1:]
+    assert _rel(out, ref.view(-1, N)) < 1e-5
+    assert torch.equal(out.view(B, P + 1, N)[:, 0], torch.zeros(B, N, device=DEV))  # CLS rows untouched
+
+
+def test_gemm_strided_rows():
+    """A operand with a row pitch (the [CLS]-row gather of the BERT pooler)."""
+    from keep_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(9, 20, 768, generator=g) * 0.5).half().to(DEV)
+    w = (torch.randn(768, 768, generator=g) * 0.05).half().to(DEV)
+    a = x[:, 0, :]  # stride 20*768
+    out = ops.gemm(a, w, ops.EPI_BIAS_F32)
+    assert _rel(out, a.float() @ w.float().T) < 1e-5
+
+
+def test_gemm_rejects_bad_shapes():
+    from keep_b200 import KeepB200Error, ops
+
+    a = torch.zeros(8, 100, dtype=torch.float16, device=DEV)
+    w = torch.zeros(128, 100, dtype=torch.float16, device=DEV)
+    with pytest.raises(KeepB200Error, match="multiple of 64"):
+        ops.gemm(a, w, ops.EPI_BIAS_F32)
+
+
+def test_layernorm_variants():
+    from keep_b200 import ops
+
+    x = torch.randn(1000, 1024, device=DEV) * 3 + 1
+    w, b = torch.rand(1024, device=DEV) + 0.5, torch.randn(1024, device=DEV)
+    y16, y32 = ops.layernorm(x, w, b, 1e-6, want_f32=True)
+    ref = F.layer_norm(x, (1024,), w, b, 1e-6)
+    assert _rel(y32, ref) < 1e-5 and _rel(y16, ref) < 1e-3
+    x2 = torch.randn(77, 768, device=DEV)
+    w2, b2 = torch.rand(768, device=DEV) + 0.5, torch.randn(768, device=DEV)
+    _, y = ops.layernorm(x2, w2, b2, 1e-12, want_f32=True)
+    assert _rel(y, F.layer_norm(x2, (768,), w2, b2, 1e-12)) < 1e-5
+    x3 = torch.randn(5, 197, 1024, device=DEV)
+    _, y = ops.layernorm(x3, w, b, 1e-6, want_f32=True, rows=5, row_stride=197 * 1024)
+    assert _rel(y, F.layer_norm(x3[:, 0], (1024,), w, b, 1e-6)) < 1e-5
+    yb, _ = ops.layernorm(x, w, b, 1e-6, out_dtype=torch.bfloat16)
+    assert yb.dtype == torch.bfloat16 and _rel(yb, ref) < 8e-3
+
+
+def test_l2norm_and_tanh():
+    from keep_b200 import ops
+
+    x = torch.randn(33, 768, device=DEV)
+    assert _rel(ops.act_l2norm(x, 0), F.normalize(x, dim=-1)) < 1e-6
+    assert _rel(ops.act_l2norm(x, 1), F.normalize(torch.tanh(x), dim=-1)) < 1e-6
+    z = torch.zeros(2, 768, device=DEV)
+    assert torch.equal(ops.act_l2norm(z, 0), z)  # eps clamp: 0 / max(0, 1e-12) = 0, no NaN
+
+
+@pytest.mark.parametrize("B,S,H,masked", [(3, 197, 16, False), (5, 256, 12, True), (7, 32, 12, True), (2, 77, 4, True),
+                                            (1, 1, 2, False), (2, 300, 2, True)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_attention(B, S, H, masked, dtype):
+    from keep_b200 import ops
+
+    g = torch.Generator().manual_seed(S * 3 + H)
+    qkv = torch.randn(B * S, 3 * H * 64, generator=g).to(dtype).to(DEV)
+    mask = None
+    bias = None
+    if masked:
+        lens = torch.randint(1, S + 1, (B,), generator=g)
+        mask = (torch.arange(S)[None, :] < lens[:, None]).long().to(DEV)
+        bias = torch.zeros(B, 1, 1, S, device=DEV).masked_fill(mask[:, None, None, :] == 0, float("-inf"))
+    out = ops.attention(qkv, B, S, H, key_mask=mask)
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, scale=0.125).transpose(1, 2).reshape(B * S, H * 64)
+    assert _rel(out, ref) < (2e-3 if dtype == torch.float16 else 1.5e-2)
+
+
+def test_similarity_and_group_softmax():
+    from keep_b200 import ops
+
+    feats = torch.randn(1000, 768, device=DEV) * 2
+    cls = F.normalize(torch.randn(768, 32, device=DEV), dim=0)
+    logits, probs = ops.similarity(feats, cls, group=2, temp=10.0)
+    ref = F.normalize(feats, dim=-1) @ cls
+    assert _rel(logits, ref) < 1e-5
+    assert _rel(probs, torch.softmax(ref.view(1000, 16, 2) * 10, -1).view(1000, 32)) < 1e-5
+    for P in (2, 3, 4, 256, 70):  # ragged prompt counts
+        c = F.normalize(torch.randn(768, P, device=DEV), dim=0)
+        lg, pr = ops.similarity(feats[:333], c)
+        r = F.normalize(feats[:333], dim=-1) @ c
+        assert _rel(lg, r) < 1e-5 and _rel(pr, torch.softmax(r * 10, 1)) < 1e-5
+    lg, pr = ops.similarity(feats[:0], cls)
+    assert lg.shape == (0, 32)
+
+
+def test_prompt_scores_chunked():
+    from keep_b200 import ops
+
+    N, K, C = 3000, 70, 4
+    feats = torch.randn(N, 768, device=DEV)
+    cls = F.normalize(torch.randn(768, K * C, device=DEV), dim=0)
+    s = ops.prompt_scores(feats, cls, K, C, workspace_mb=1)  # forces several row chunks
+    lg = (F.normalize(feats, dim=-1) @ cls).view(N, K, C)
+    top = lg.topk(2, dim=2).values
+    ref = ((top[..., 0] - top[..., 1]) - (top[..., 0] + top[..., 1] - 1).abs()).mean(0)
+    assert (s - ref).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("overlap", [True, False])
+@pytest.mark.parametrize("C", [2, 4])
+def test_refine_bit_exact_vs_dict_walk(overlap, C):
+    """Integer/index work and the float32 neighbour mean must equal the reference's dict walk bit for bit."""
+    from keep_b200 import ops
+    from oracle import wsi_oracle as wo
+
+    g = torch.Generator().manual_seed(5 + C)
+    N = 20000
+    xy = torch.randint(0, 90, (N, 2), generator=g) * 224  # duplicates (first wins) and holes
+    probs = torch.softmax(torch.randn(N, C, generator=g), 1)
+    keep, refined = ops.refine(xy.to(DEV), probs.to(DEV), 224, overlap)
+    exp = wo.refine_mean(probs.numpy(), xy.numpy(), 224, overlap)
+    first = wo._first_occurrence(xy.numpy())
+    exp_keep = np.zeros(N, dtype=np.uint8)
+    exp_keep[list(first.values())] = 1
+    assert np.array_equal(keep.cpu().numpy(), exp_keep)
+    got = refined.cpu().numpy()
+    for (x, y), i in first.items():
+        assert np.array_equal(got[i], exp[(x, y)]), (x, y)

@@ -1,0 +1,118 @@
+"""GPU: the WSI_evaluation entry points (keep_b200.wsi) against the golden vectors produced by the reference's
+own functions (tests/golden/wsi.npz) and against the CPU oracle restatement."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import wsi_oracle as wo
+from oracle.fake_tokenizer import FakeTokenizer
+from tests import common
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def data():
+    feats, coords, cls2, cls4, bank = common.wsi_inputs()
+    return feats.to(DEV), coords, cls2.to(DEV), cls4.to(DEV), [b.to(DEV) for b in bank]
+
+
+def test_tile_probabilities(data, golden_dir):
+    from keep_b200 import wsi
+
+    g = common.load_golden(golden_dir, "wsi.npz")
+    feats, _, cls2, _, _ = data
+    logits, probs = wsi.tile_probabilities(cls2, feats)
+    assert np.abs(probs[:64].cpu().numpy() - g["probs2_head"]).max() < 1e-5
+    ref_logits, ref_probs = wo.tile_probs(cls2.cpu(), feats.cpu())
+    assert (logits.cpu() - ref_logits).abs().max() < 1e-5
+    labels_agree = (probs.argmax(1).cpu() == ref_probs.argmax(1)).float().mean().item()
+    assert labels_agree >= 0.999
+
+
+def test_detection_matches_reference(data, golden_dir):
+    from keep_b200 import wsi
+
+    g = common.load_golden(golden_dir, "wsi.npz")
+    feats, coords, cls2, _, _ = data
+    assert wsi.zero_shot_detection(cls2, feats, coords, patch_size=112, overlap=False) == pytest.approx(float(g["det_frac_no_overlap"]), abs=2 / 978)
+    assert wsi.zero_shot_detection(cls2, feats, coords, patch_size=112, overlap=True) == pytest.approx(float(g["det_frac_overlap"]), abs=2 / 978)
+    _, probs = wsi.tile_probabilities(cls2, feats)
+    preds, pr = wsi.refine_seg_detection(probs, coords, patch_size=112, overlap=True)
+    assert list(preds.keys()) == g["det_keys"].tolist()                      # same tiles, same (insertion) order
+    assert np.abs(np.array(list(pr.values())) - g["det_probs"]).max() < 1e-5
+    assert (np.array(list(preds.values())) == g["det_preds"]).mean() >= 0.998
+
+
+def test_subtyping_and_segment_match_reference(data, golden_dir):
+    from keep_b200 import wsi
+
+    g = common.load_golden(golden_dir, "wsi.npz")
+    feats, coords, cls2, cls4, _ = data
+    label = wsi.zero_shot_subtyping(cls4, feats, coords, patch_size=112, overlap=True)
+    assert label.dtype == torch.int64 and int(label) == int(g["sub_label"])
+    _, probs4 = wsi.tile_probabilities(cls4, feats)
+    sp = wsi.refine_seg_subtyping(probs4, coords, patch_size=112, overlap=True)
+    assert (np.array(list(sp.values())) == g["sub_preds"]).mean() >= 0.998
+    sg = wsi.zero_shot_segment_probs(cls2, feats, coords, patch_size=112, overlap=True)
+    assert np.abs(np.array(list(sg.values())) - g["seg_probs"]).max() < 1e-5
+
+
+def test_prompt_screening_matches_reference(data, golden_dir):
+    from keep_b200 import wsi
+
+    g = common.load_golden(golden_dir, "wsi.npz")
+    feats, _, _, _, bank = data
+    scores = wsi.prompt_scores(bank, feats).cpu().numpy()
+    assert np.abs(scores - g["select_scores"]).max() < 1e-5
+    merged = wsi.zero_shot_prompt_select(bank, feats, topn=5, device=DEV)
+    assert np.abs(merged.cpu().numpy() - g["select_merged"]).max() < 1e-5
+    assert wsi.rank_cls_score(torch.nn.functional.normalize(feats, dim=-1) @ bank[3]) == pytest.approx(float(g["select_scores"][3]), abs=1e-5)
+
+
+def test_classifier_construction_matches_reference(golden_dir):
+    """get_zeroshot_classifier through the product model (tiny towers, fake tokenizer) vs the reference code's
+    output on the same weights, incl. label ordering, add_normal and the first-template quirk."""
+    from keep_b200 import wsi
+
+    g = common.load_golden(golden_dir, "wsi.npz")
+    _, sd, text_cfg = common.tiny_oracle(seed=2, max_pos=256)
+    prod = common.tiny_product(sd, text_cfg)
+    KEEP = {"model": prod, "tokenizer": FakeTokenizer(1000)}
+    prompts = {"classnames": {"Tumor": "tumor tissue", "Normal": "normal tissue", "CCRCC": "clear cell renal cell carcinoma"},
+               "templates": "CLASSNAME."}
+    c1 = wsi.get_zeroshot_classifier(KEEP, {"Normal": 0, "Tumor": 1}, prompts, DEV)
+    c2 = wsi.get_zeroshot_classifier(KEEP, {"CCRCC": 0, "Tumor": 1}, prompts, DEV, add_normal=True)
+    multi = {"classnames": prompts["classnames"], "templates": ["a photo of CLASSNAME.", "CLASSNAME, H&E."]}
+    c3 = wsi.get_zeroshot_classifier(KEEP, {"Normal": 0, "Tumor": 1}, multi, DEV)
+    for got, key in ((c1, "classifier_basic"), (c2, "classifier_add_normal"), (c3, "classifier_multi_template")):
+        ref = torch.from_numpy(g[key])
+        assert got.shape == ref.shape
+        rl, cos = common.row_metrics(got.t(), ref.t())
+        assert rl <= 2e-3 and cos >= 0.99999, (key, rl, cos)
+    # batched bank == per-prompt construction
+    bank_prompts = {"0": prompts, "1": {"classnames": {"Tumor": "malignant tumor", "Normal": "normal tissue"}, "templates": "CLASSNAME."}}
+    bank = wsi.build_classifier_bank(KEEP, {"Normal": 0, "Tumor": 1}, bank_prompts, DEV)
+    assert (bank[0] - c1).abs().max().item() < 1e-4
+    ref1 = wsi.get_zeroshot_classifier(KEEP, {"Normal": 0, "Tumor": 1}, bank_prompts["1"], DEV)
+    assert (bank[1] - ref1).abs().max().item() < 1e-4
+
+
+def test_raw_tiles_through_task_head(golden_dir):
+    """tile_features given as raw tiles: encode_image feeds the similarity/refine path."""
+    from keep_b200 import wsi
+
+    oracle, sd, text_cfg = common.tiny_oracle(seed=1)
+    prod = common.tiny_product(sd, text_cfg)
+    g = torch.Generator().manual_seed(4)
+    tiles = torch.randn(12, 3, 224, 224, generator=g)
+    coords = np.stack([np.arange(12) % 4 * 224, np.arange(12) // 4 * 224], 1)
+    cls = torch.nn.functional.normalize(torch.randn(128, 2, generator=g), dim=0)
+    with torch.no_grad():
+        feats = oracle.encode_image(tiles)
+    exp = wo.zero_shot_detection(cls, feats, coords, patch_size=224, overlap=True)
+    got = wsi.zero_shot_detection(cls.to(DEV), tiles.to(DEV), coords, patch_size=224, overlap=True, model=prod)
+    assert abs(got - exp) <= 1 / 12 + 1e-9
+    with pytest.raises(ValueError):
+        wsi.zero_shot_detection(cls.to(DEV), tiles.to(DEV), coords)
