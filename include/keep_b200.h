@@ -141,6 +141,15 @@ int keepb200_refine(const int64_t* coords, const float* probs, int64_t N, int64_
                     uint8_t* keep, float* refined, void* workspace, size_t workspace_bytes, void* stream);
 size_t keepb200_refine_workspace_bytes(int64_t N);
 
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------------------ */
+/* Number of kernels this library has launched in this process (every launcher counts its launches). */
+int64_t keepb200_launch_count(void);
+/* Between begin and end every tcgen05 GEMM launch is bracketed with CUDA events on its launching stream.
+ * end() synchronises the device and returns the summed GEMM device time (ms), the algorithmic FLOPs
+ * (2*M*N*K per launch) of those launches, their count, and the count of ALL kernels launched in between. */
+int keepb200_profile_begin(void);
+int keepb200_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches, int64_t* all_launches);
+
 /* ---- single-kernel entry points (unit tests and profiling) ------------------------------------------- */
 /* out = epilogue(A[M,K] . W[N,K]^T); epi: 0 bias->16-bit, 1 bias+GELU(erf)->16-bit,
  * 2 resid + gamma*(acc+bias) -> fp32, 3 bias -> fp32, 4 ViT patch-embed scatter (+pos) -> fp32 */

@@ -550,6 +550,16 @@ int keepb200_refine(const int64_t* coords, const float* probs, int64_t N, int64_
                        static_cast<cudaStream_t>(stream));
 }
 
+int keepb200_profile_begin(void) { return profile_begin(); }
+int keepb200_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches, int64_t* all_launches) {
+  long long gl = 0, al = 0;
+  int rc = profile_end(gemm_ms, gemm_flops, &gl, &al);
+  if (gemm_launches) *gemm_launches = gl;
+  if (all_launches) *all_launches = al;
+  return rc;
+}
+int64_t keepb200_launch_count(void) { return launch_count(); }
+
 // ---- single-kernel entry points -----------------------------------------------------------------------------------
 int keepb200_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epi, int bf16,
                      const float* bias, const float* gamma, const float* resid, int64_t ldr, void* out, int64_t ldo,

@@ -246,6 +246,7 @@ int launch_attention(const void* qkv, void* out, int B, int S, int H, int bf16, 
   else
     attention_kernel<false><<<grid, kAttThreads, smem, stream>>>((const uint16_t*)qkv, (uint16_t*)out, S, H,
                                                                  (const long long*)key_mask, mask_stride, scale_log2);
+  note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }

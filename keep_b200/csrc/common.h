@@ -27,6 +27,17 @@ const char* last_error();
 
 int num_sms();
 
+// ---- launch accounting / live GEMM timing (bench.py: gpu_launches and roofline.achieved) ----------------
+// Every launcher calls note_launch() once per kernel launch. While profiling is on, launch_gemm brackets each
+// GEMM launch with CUDA events on the launching stream; profile_end() synchronises and sums them.
+void note_launch(int n = 1);
+long long launch_count();
+bool profiling();
+void profile_gemm_begin(cudaStream_t s);
+void profile_gemm_end(cudaStream_t s, double flops);
+int profile_begin();
+int profile_end(double* gemm_ms, double* gemm_flops, long long* gemm_launches, long long* all_launches);
+
 // ---- TMA tensor maps ---------------------------------------------------------------------------
 // 2-D row-major matrix [rows, cols] of 2- or 4-byte elements with row pitch `ld` elements, box =
 // [box_rows, 128 bytes] and SWIZZLE_128B. Cached by value of all arguments.

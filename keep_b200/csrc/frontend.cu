@@ -147,6 +147,7 @@ bert_embed_kernel(const long long* __restrict__ ids, const long long* __restrict
 static int launch_cls_rows(const float* cls, const float* pos, float* x, int64_t B, int T, int D, cudaStream_t stream) {
   const long long n = (long long)B * D;
   cls_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cls, pos, x, B, T, D);
+  note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }
@@ -160,6 +161,7 @@ int launch_im2col(const float* tiles, int64_t B, int G, void* patches16, int bf1
   const long long cap = (long long)num_sms() * 32;
   if (blocks > cap) blocks = cap;
   im2col_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tiles, total, G, (uint16_t*)patches16, bf16);
+  note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return launch_cls_rows(cls, pos, x, B, G * G + 1, D, stream);
 }
@@ -173,6 +175,7 @@ int launch_im2col_u8(const uint8_t* tiles, int64_t B, int G, void* patches16, in
   const long long cap = (long long)num_sms() * 32;
   if (blocks > cap) blocks = cap;
   im2col_u8_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tiles, total, G, (uint16_t*)patches16, bf16);
+  note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return launch_cls_rows(cls, pos, x, B, G * G + 1, D, stream);
 }
@@ -199,6 +202,7 @@ int launch_bert_embed(const int64_t* ids, const int64_t* tts, int64_t id_stride,
     default: KB_EMB(8); break;
   }
 #undef KB_EMB
+  note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }

@@ -282,7 +282,10 @@ int launch_one(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, 
   const int tiles = m_tiles * n_tiles;
   int grid = num_sms();
   if (tiles < grid) grid = tiles;
+  profile_gemm_begin(stream);
   gemm_kernel<BN, EPI><<<grid, kThreads, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  profile_gemm_end(stream, 2.0 * a.M * a.N * a.K);
+  note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }

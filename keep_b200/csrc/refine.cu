@@ -123,6 +123,7 @@ int launch_refine(const int64_t* coords, const float* probs, int64_t N, int C, i
   table_insert_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>((const long long*)coords, N, keys, vals, cap - 1);
   refine_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>((const long long*)coords, probs, N, C, ps, overlap, keys,
                                                                  vals, cap - 1, keep, refined);
+  note_launch(3);
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }

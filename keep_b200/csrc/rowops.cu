@@ -141,6 +141,7 @@ int launch_layernorm(const float* x, int64_t x_row_stride, int64_t rows, int D, 
   const unsigned grid = (unsigned)((rows + 7) / 8);
   KB_DISPATCH_NV(D / 128, (layernorm_kernel<NV><<<grid, 256, 0, stream>>>(x, x_row_stride, rows, w, b, eps,
                                                                           (uint16_t*)y16, bf16, y32)));
+  note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }
@@ -150,6 +151,7 @@ int launch_act_l2norm(const float* x, int64_t rows, int D, int act, float* y, cu
   if (D % 128 != 0) return set_error(KB_ERR_ARG, "l2norm: D=%d must be a multiple of 128", D);
   const unsigned grid = (unsigned)((rows + 7) / 8);
   KB_DISPATCH_NV(D / 128, (act_l2norm_kernel<NV><<<grid, 256, 0, stream>>>(x, rows, act, y)));
+  note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }
@@ -161,6 +163,7 @@ int launch_cast_f32_to_16(const float* src, void* dst, int64_t n, int bf16, cuda
   unsigned grid = (unsigned)((n4 + 255) / 256);
   if (grid > (unsigned)num_sms() * 16) grid = num_sms() * 16;
   cast_kernel<<<grid, 256, 0, stream>>>(src, (uint16_t*)dst, n4, bf16);
+  note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }
@@ -169,6 +172,7 @@ int launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaS
   if (rows <= 0 || cols <= 0) return KB_OK;
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   transpose_kernel<<<grid, block, 0, stream>>>(src, dst, rows, cols);
+  note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 namespace kb {
 
@@ -30,6 +31,61 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch accounting and live GEMM timing
+// ---------------------------------------------------------------------------------------------------
+static long long g_launches = 0;
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_ev_pool;  // pairs: [2i] start, [2i+1] stop
+static size_t g_ev_used = 0;
+static double g_prof_flops = 0.0;
+static long long g_prof_launch_base = 0;
+
+void note_launch(int n) { g_launches += n; }
+long long launch_count() { return g_launches; }
+bool profiling() { return g_prof_on; }
+
+void profile_gemm_begin(cudaStream_t s) {
+  if (!g_prof_on) return;
+  if (g_ev_used + 2 > g_ev_pool.size()) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    g_ev_pool.push_back(a);
+    g_ev_pool.push_back(b);
+  }
+  cudaEventRecord(g_ev_pool[g_ev_used], s);
+}
+void profile_gemm_end(cudaStream_t s, double flops) {
+  if (!g_prof_on) return;
+  cudaEventRecord(g_ev_pool[g_ev_used + 1], s);
+  g_ev_used += 2;
+  g_prof_flops += flops;
+}
+int profile_begin() {
+  g_prof_on = true;
+  g_ev_used = 0;
+  g_prof_flops = 0.0;
+  g_prof_launch_base = g_launches;
+  return KB_OK;
+}
+int profile_end(double* gemm_ms, double* gemm_flops, long long* gemm_launches, long long* all_launches) {
+  g_prof_on = false;
+  KB_CUDA_CHECK(cudaDeviceSynchronize());
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < g_ev_used; i += 2) {
+    float t = 0.f;
+    KB_CUDA_CHECK(cudaEventElapsedTime(&t, g_ev_pool[i], g_ev_pool[i + 1]));
+    ms += t;
+  }
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_flops) *gemm_flops = g_prof_flops;
+  if (gemm_launches) *gemm_launches = (long long)(g_ev_used / 2);
+  if (all_launches) *all_launches = g_launches - g_prof_launch_base;
+  g_ev_used = 0;
+  return KB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------

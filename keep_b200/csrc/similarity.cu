@@ -138,10 +138,12 @@ int launch_similarity(const float* feats, int64_t N, int D, const float* cls, in
   if (P % group != 0) return set_error(KB_ERR_ARG, "similarity: P=%d is not a multiple of group=%d", P, group);
   dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)((P + BN - 1) / BN));
   sim_gemm_kernel<<<grid, 256, 0, stream>>>(feats, N, D, cls, P, logits);
+  note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   if (probs != nullptr) {
     const long long n = N * (P / group);
     group_softmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(logits, N, P, group, temp, probs);
+    note_launch();
     KB_CUDA_CHECK(cudaGetLastError());
   }
   return KB_OK;
@@ -152,6 +154,7 @@ int launch_prompt_score_accum(const float* logits, int64_t rows, int K, int C, f
   if (C < 2) return set_error(KB_ERR_ARG, "prompt scores: need at least 2 classes per classifier (got %d)", C);
   dim3 grid((unsigned)((K + 31) / 32), (unsigned)((rows + 255) / 256));
   prompt_score_kernel<<<grid, 256, 0, stream>>>(logits, rows, K, C, scores);
+  note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }
@@ -159,6 +162,7 @@ int launch_prompt_score_accum(const float* logits, int64_t rows, int K, int C, f
 int launch_scale(float* v, int64_t n, float s, cudaStream_t stream) {
   if (n <= 0) return KB_OK;
   scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(v, n, s);
+  note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }

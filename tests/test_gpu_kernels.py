@@ -64,7 +64,11 @@ def test_gemm_gelu_is_exact_erf():
     out = ops.gemm(a, w, ops.EPI_BIAS_GELU_HALF, bias=bias)
     pre = a.float() @ w.float().T + bias
     assert _rel(out, F.gelu(pre)) < 1e-3
-    assert _rel(out, F.gelu(pre, approximate="tanh")) > _rel(out, F.gelu(pre))
+    # the tanh approximation differs from erf-GELU by up to 4.7e-4, systematically: visible in the mean error
+    err_erf = (out.float() - F.gelu(pre)).abs().mean().item()
+    err_tanh = (out.float() - F.gelu(pre, approximate="tanh")).abs().mean().item()
+    assert err_erf < 0.8 * err_tanh, (err_erf, err_tanh)
+    assert abs((out.float() - F.gelu(pre)).mean().item()) < 5e-6
 
 
 def test_gemm_residual_layerscale_in_place():
