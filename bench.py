@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — WSI tiles/sec of the KEEP zero-shot hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], `zeroshot_detection_WSI.py`): 10,000 synthetic 224x224x3 tiles x 32 prompt
+columns (16 two-class classifiers) per GPU, streamed in batches of 1024.  One STEP = one pass of the hot path over
+that slide:  tiles -> encode_image (ViT-L/16 + visual_head + L2-normalise) -> [N,768] -> normalise @ classifier
+-> softmax(x10) -> [N,32] probabilities (+ one all-gather of the probabilities when N_gpus > 1).
+The 32 prompt embeddings are produced once by encode_text before the timed region, as the reference scripts do
+(classifiers are built once per slide; WSI_evaluation/zeroshot_detection_WSI.py:50-53).
+
+  value  : tiles/s with the tiles already resident in HBM (device-timed, max over ranks)
+  e2e    : the same pass through the public API with the tiles in PINNED HOST memory: every batch is copied
+           host->device inside the timed region (double-buffered on a copy stream) and the [N,32]
+           probabilities are copied back device->host
+  roofline: the tcgen05 GEMM kernels (97% of the algorithmic FLOPs): sum(2MNK) / sum(device time of the GEMM
+           launches), both measured live with CUDA events around every GEMM launch in the timed region
+  cpu_baseline / --impl reference: the CPU oracle port of the reference (oracle/keep_oracle.py: the reference
+           KEEPModel semantics + restated timm ViT-L/16; timm is not installed) on the host cores, fp32.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "WSI tiles/sec (224x224, ViT-L/16) zero-shot hot path"
+UNIT = "tiles/s"
+FLOP_PER_TILE = 123.110e9  # SURVEY.md §8d / BASELINE.md §2: ViT-L/16 + visual_head, MAC = 2 FLOP, 197 tokens
+N_TILES, N_PROMPTS, BATCH = 10_000, 32, 1024
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"tflops_sustained": d["bf16_tflops_sustained"], "tflops_burst": d["bf16_tflops"], "hbm_gbs": d["hbm_gbs"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# -------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference, timed on the host cores
+# -------------------------------------------------------------------------------------------------------------
+def cpu_reference_tiles_per_s(sample_tiles: int, steps: int, warmup: int):
+    """encode_image + similarity on the CPU for `sample_tiles` tiles per step (fp32, all host threads)."""
+    from oracle import keep_oracle as ko  # the ONLY place bench.py touches oracle/: the CPU baseline legs
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = ko.KEEPModel(ko.DEFAULT_TEXT_CONFIG, 768, ko.DEFAULT_VISION_CONFIG).eval()
+    model.load_state_dict(ko.synthetic_state_dict(model, seed=0))
+    g = torch.Generator().manual_seed(1234)
+    tiles = torch.randn(sample_tiles, 3, 224, 224, generator=g)
+    cls = torch.nn.functional.normalize(torch.randn(768, N_PROMPTS, generator=g), dim=0)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            feats = model.encode_image(tiles)
+            logits = torch.nn.functional.normalize(feats, dim=-1) @ cls
+            probs = torch.softmax(logits.view(sample_tiles, N_PROMPTS // 2, 2) * 10, dim=-1)
+            _ = float(probs.sum())
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    cpu_name = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                cpu_name = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return sample_tiles / sec, sec * 1e3, threads, cpu_name
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return 0
+    sample = 16
+    tps, ms, threads, cpu = cpu_reference_tiles_per_s(sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(), "note": "reference = CPU fp32 path of KEEPModel.encode_image + similarity; timm is "
+                   "un-vendored and not installed, so the ViT-L/16 is the oracle's restatement (oracle/keep_oracle.py)"},
+        "cpu_baseline": {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} tiles per step (encode_image + 32-prompt similarity), fp32, {cpu}"},
+        "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_name():
+    return (f"zeroshot_detection_WSI (BASELINE configs[1]): {N_TILES} synthetic 224x224 tiles x {N_PROMPTS} prompts "
+            f"(16 classifiers x 2) per GPU, batches of {BATCH}")
+
+
+# -------------------------------------------------------------------------------------------------------------
+# GPU arm
+# -------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="keep_b200", choices=["keep_b200", "reference"])
+    ap.add_argument("--tiles", type=int, default=N_TILES, help="tiles per GPU per step (default = the BASELINE config)")
+    ap.add_argument("--operand-dtype", default="float16", choices=["float16", "bfloat16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "keep_b200" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank)
+
+    from keep_b200 import KEEPConfig, KEEPModel, _lib, ops
+    from keep_b200 import distributed as kd
+    from keep_b200.weights import random_state_dict
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: keep_b200 has no CPU path")
+    kd.init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    L = _lib.lib()
+    n_tiles = args.tiles
+
+    # ---- model with random-init weights of the reference architecture (no checkpoint offline) ----
+    cfg = KEEPConfig(operand_dtype=args.operand_dtype)
+    with torch.device(dev):
+        model = KEEPModel(cfg)
+    model.load_state_dict(random_state_dict(cfg, seed=0, device=dev), strict=True)
+    model.eval()
+
+    # ---- inputs: tiles resident in HBM (6.0 GB > 126 MB L2), 32 prompts -> 16 two-class classifiers ----
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    tiles = torch.empty(n_tiles, 3, 224, 224, dtype=torch.float32, device=dev)
+    for b0 in range(0, n_tiles, BATCH):
+        tiles[b0:b0 + BATCH].normal_(generator=g)
+    ids = torch.zeros(N_PROMPTS, 256, dtype=torch.long, device=dev)
+    mask = torch.zeros_like(ids)
+    gl = torch.Generator().manual_seed(3000)
+    for i in range(N_PROMPTS):
+        n = int(torch.randint(4, 33, (1,), generator=gl))
+        ids[i, 0], ids[i, n - 1] = 2, 3
+        ids[i, 1:n - 1] = torch.randint(5, 30522, (n - 2,), generator=gl).to(dev)
+        mask[i, :n] = 1
+    text = model.encode_text({"input_ids": ids, "token_type_ids": torch.zeros_like(ids), "attention_mask": mask})
+    classifier = text.t().contiguous()  # [768, 32]: column pairs are the 16 classifiers
+
+    probs_out = torch.empty(n_tiles, N_PROMPTS, dtype=torch.float32, device=dev)
+
+    def step_resident():
+        for b0 in range(0, n_tiles, BATCH):
+            feats = model.encode_image(tiles[b0:b0 + BATCH])
+            _, pr = ops.similarity(feats, classifier, group=2, temp=10.0)
+            probs_out[b0:b0 + BATCH] = pr
+        return _gather(probs_out) if world > 1 else probs_out
+
+    gather_buf = torch.empty(world * n_tiles, N_PROMPTS, dtype=torch.float32, device=dev) if world > 1 else None
+
+    def _gather(local_probs):
+        torch.distributed.all_gather_into_tensor(gather_buf, local_probs)  # the path's single collective
+        return gather_buf
+
+    def timed(fn, steps):
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+        return kd.barrier_max_ms(e0.elapsed_time(e1), dev)
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _lib.check(L.keepb200_profile_begin(), "profile_begin")
+    ms_total = timed(step_resident, args.steps)
+    gemm_ms, gemm_flops, gemm_n, all_n = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
+    _lib.check(L.keepb200_profile_end(C.byref(gemm_ms), C.byref(gemm_flops), C.byref(gemm_n), C.byref(all_n)), "profile_end")
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * n_tiles / (ms_step / 1e3)
+
+    # ---- e2e: tiles in pinned host memory, H2D per batch inside the timed region, probabilities back to host ----
+    e2e = None
+    if not args.no_e2e:
+        host_tiles = torch.empty(n_tiles, 3, 224, 224, dtype=torch.float32, pin_memory=True)
+        host_tiles.copy_(tiles)
+        host_probs = torch.empty(n_tiles, N_PROMPTS, dtype=torch.float32, pin_memory=True)
+        stage = [torch.empty(BATCH, 3, 224, 224, dtype=torch.float32, device=dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(dev)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+
+        def step_e2e():
+            main = torch.cuda.current_stream(dev)
+            starts = list(range(0, n_tiles, BATCH))
+            for i, b0 in enumerate(starts):
+                n = min(BATCH, n_tiles - b0)
+                s = i & 1
+                with torch.cuda.stream(copy_stream):
+                    if i >= 2:
+                        copy_stream.wait_event(freed[s])
+                    stage[s][:n].copy_(host_tiles[b0:b0 + n], non_blocking=True)
+                    ready[s].record(copy_stream)
+                main.wait_event(ready[s])
+                feats = model.encode_image(stage[s][:n])
+                _, pr = ops.similarity(feats, classifier, group=2, temp=10.0)
+                freed[s].record(main)
+                probs_out[b0:b0 + n] = pr
+            res = _gather(probs_out) if world > 1 else probs_out
+            host_probs.copy_(res[rank * n_tiles:(rank + 1) * n_tiles] if world > 1 else res, non_blocking=True)
+            main.synchronize()  # the caller holds the step's result on the host
+
+        step_e2e()
+        ms_e2e = timed(step_e2e, args.steps) / args.steps
+        e2e = {"value": world * n_tiles / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(n_tiles * 3 * 224 * 224 * 4),
+               "d2h_bytes_per_step": int(n_tiles * N_PROMPTS * 4), "ms_per_step": ms_e2e,
+               "api": "KEEPModel.encode_image + ops.similarity on pinned-host fp32 tiles, double-buffered H2D"}
+        del host_tiles, stage
+
+    # ---- CPU baseline beside it (rank 0, single-GPU run only) ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del tiles
+        torch.cuda.empty_cache()
+        tps, ms_cpu, threads, cpu = cpu_reference_tiles_per_s(32, steps=2, warmup=1)
+        cpu_baseline = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"32 tiles per iteration x 2 timed iterations (1 warm-up), encode_image + similarity, fp32, {cpu}"}
+
+    if rank == 0:
+        peaks = measured_peaks()
+        ach = gemm_flops.value / (gemm_ms.value / 1e3) / 1e12 if gemm_ms.value > 0 else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16" if args.operand_dtype == "float16" else "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(), "tiles_per_gpu_per_step": n_tiles, "prompts": N_PROMPTS, "batch": BATCH,
+                       "image_chunk": model.image_chunk, "operands": args.operand_dtype + " (fp32 accumulate/residual/LN/softmax)",
+                       "weights": "random-init ViT-L/16 + BERT-base (no checkpoint offline)",
+                       "l2": f"no flush needed: each step streams {n_tiles * 602112 / 1e9:.1f} GB of tiles (>> 126 MB L2)",
+                       "parallelism": f"dp{world} tile-shard, one all-gather of [N,{N_PROMPTS}] probabilities" if world > 1 else "single GPU"},
+            "roofline": {"bound": "tensor", "kernel": "kb::gemm_kernel<BN,EPI> (tcgen05/TMA GEMM, all dense layers)",
+                         "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": (ach / peaks["tflops_sustained"]) if ach else None, "traffic": traffic,
+                         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                         "gemm_share_of_step": gemm_ms.value / ms_total if ms_total else None,
+                         "gemm_launches": gemm_n.value,
+                         "whole_path_frac": value * FLOP_PER_TILE / (world * peaks["tflops_sustained"] * 1e12)},
+            "e2e": e2e, "gpu_launches": int(all_n.value), "clocks": clocks,
+        }
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

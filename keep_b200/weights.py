@@ -71,3 +71,38 @@ def state_dict_spec(config) -> "OrderedDict[str, tuple]":
 
 # buffers that some transformers versions serialise with BertModel; accepted and ignored on load
 IGNORED_BUFFERS = ("text.embeddings.position_ids", "text.embeddings.token_type_ids")
+
+
+def random_state_dict(config, seed: int = 0, device="cpu"):
+    """Random-init weights of the right architecture for benchmarks and smoke runs (no checkpoint is available
+    offline): linear weights N(0, 1/fan_in), LayerNorm weights 1 +- 0.1, LayerScale U(0.05, 0.5) so that every
+    block contributes, small biases/embeddings. Generated directly on `device`."""
+    import math
+
+    import torch
+
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = {}
+    for name, shape in state_dict_spec(config).items():
+        leaf = name.rsplit(".", 1)[-1]
+        if name == "logit_scale":
+            t = torch.tensor(math.log(1 / 0.04), device=device)
+        elif leaf == "gamma":
+            t = torch.rand(shape, generator=g, device=device) * 0.45 + 0.05
+        elif "norm" in name.lower() and leaf == "weight":
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g, device=device)
+        elif leaf == "bias":
+            t = 0.02 * torch.randn(shape, generator=g, device=device)
+        elif leaf == "cls_token":
+            t = 0.02 * torch.randn(shape, generator=g, device=device)
+        elif leaf == "pos_embed":
+            t = 0.1 * torch.randn(shape, generator=g, device=device)
+        elif "embeddings" in name:
+            t = 0.05 * torch.randn(shape, generator=g, device=device)
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            t = torch.randn(shape, generator=g, device=device) / math.sqrt(fan_in)
+        out[name] = t.float()
+    return out
