@@ -1,18 +1,30 @@
-// Persistent warp-specialised GEMM for sm_100a:  out = epilogue(A[M,K] . W[N,K]^T)
+// Persistent warp-specialised GEMMs for sm_100a:  out = epilogue(A[M,K] . W[N,K]^T)
 //
-//   * operands fp16 or bf16 (K-major, i.e. activations [M,K] row-major and torch Linear weights [N,K]),
-//     fp32 accumulation in TMEM via tcgen05.mma.kind::f16 (UMMA 128 x BLOCK_N x 16);
-//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) stages 128x64 / BLOCK_Nx64 tiles through a
-//     kStages-deep mbarrier ring; one producer thread, one MMA-issuing thread;
-//   * the accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i
-//     overlaps the main loop of tile i+1; 8 epilogue warps drain it with tcgen05.ld and apply the
-//     fused epilogue (bias / exact-erf GELU / LayerScale + fp32 residual / patch-embed scatter).
+//   * operands fp16 or bf16 (K-major: activations [M,K] row-major, torch Linear weights [N,K]), fp32
+//     accumulation in TMEM via tcgen05.mma.kind::f16;
+//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) stages the operand tiles through an mbarrier ring; one
+//     producer thread and one MMA-issuing thread per CTA (pair);
+//   * the accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
+//     main loop of tile i+1;
+//   * 8 epilogue warps drain TMEM with tcgen05.ld, transpose 32x32 blocks through warp-private XOR-swizzled
+//     shared memory so that every global access (fp32 residual read-modify-write, 16-bit stores) is a
+//     row-contiguous 64/128-byte segment, and apply the fused epilogue (bias / exact-erf GELU /
+//     LayerScale + fp32 residual / patch-embed scatter + pos_embed).
 //
-// This one kernel serves every dense layer on the path: ViT patch-embed, qkv, proj, fc1, fc2, the
-// visual_head, and the BERT q|k|v, attention-output, intermediate, output and pooler projections
-// (reference call sites: quick_start/keep_inference.py:32-46,49-50; SURVEY.md §2.3 K1,K3,K5-K8,K10,K11).
+// Two main-loop variants:
+//   gemm_kernel<BN,EPI>   one CTA per tile, UMMA 128 x BN x 16 (cta_group::1) — small problems
+//   gemm2_kernel<EPI>     a CTA PAIR (cluster of 2) per 256x256 tile, UMMA 256 x 256 x 16 (cta_group::2):
+//                         each CTA stages its 128 rows of A and its 128 rows of W, so per-SM operand traffic
+//                         (L2->SMEM and SMEM->tensor core) drops by a third against the 128x256 single-CTA tile
+//
+// These kernels serve every dense layer on the path: ViT patch-embed, qkv, proj, fc1, fc2, the visual_head,
+// and the BERT q|k|v, attention-output, intermediate, output and pooler projections (reference call sites:
+// quick_start/keep_inference.py:32-46,49-50; SURVEY.md §2.3 K1,K3,K5-K8,K10,K11).
 #include "common.h"
 #include "ptx.cuh"
+
+#include <cstdlib>
+#include <cstring>
 
 namespace kb {
 
@@ -24,17 +36,8 @@ constexpr int UMMA_K = 16;
 constexpr int kNumEpiWarps = 8;
 constexpr int kFirstEpiWarp = 4;
 constexpr int kThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;  // 384
-
-template <int BN>
-struct Cfg {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;       // 32 KB @ BN=256
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256: power of two
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
-};
+constexpr int kStageTileBytes = 32 * 32 * 4;                   // per-warp 32x32 fp32 transpose tile
+constexpr int kEpiSmemBytes = kNumEpiWarps * kStageTileBytes;  // 32 KB
 
 struct KParams {
   int M, N, K;
@@ -50,9 +53,21 @@ struct KParams {
   int bf16;
 };
 
+// erf with |error| <= ~3e-7 (Abramowitz-Stegun 7.1.26 + fast reciprocal/exp2): far below the 16-bit rounding
+// of the stored activation, at about half the instruction count of erff().
+__device__ __forceinline__ float erf_fast(float z) {
+  const float a = fabsf(z);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, a, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float e = exp2f(-1.4426950408889634f * a * a);
+  return copysignf(fmaf(-p * t, e, 1.0f), z);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  // exact (erf) GELU as torch.nn.GELU() default: 0.5 x (1 + erf(x / sqrt(2)))
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  // exact-erf GELU, torch.nn.GELU() default: 0.5 x (1 + erf(x / sqrt(2)))
+  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f));
 }
 
 __device__ __forceinline__ uint32_t pack16(float a, float b, int bf16) {
@@ -64,16 +79,104 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int bf16) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Drain one warp's share of an accumulator tile: TMEM lanes [32q, 32q+32) x columns [c_begin, c_end) of the
+// accumulator at `tmem_acc`; rows row0.. of the output, tile column base n0.
+template <int EPI>
+__device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_acc, int q, int lane, int row0, int n0,
+                                              int c_begin, int c_end, uint8_t* stage) {
+  const uint32_t stage_addr = smem_u32(stage);
+  // transposed role of this lane: rows 4i + (lane >> 3), columns 4*(lane & 7) .. +3 of the 32x32 block
+  const int tr = lane >> 3, tc = (lane & 7) * 4;
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    const int col = n0 + c0;
+    if (col >= p.N) break;  // warp-uniform; N is a multiple of 32
+    float4 res[8];
+    if constexpr (EPI == EPI_RESID_F32) {
+      // issue the residual reads first: they do not depend on the accumulator
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = row0 + 4 * i + tr;
+        res[i] = (r < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)r * p.ldr + col + tc)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
+    tmem_ld_wait();
+    // own row `lane` -> staging, 16-byte chunk j at (j ^ (lane & 7)): conflict-free for both access patterns
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t a = stage_addr + lane * 128 + ((j ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * j]), "r"(v[4 * j + 1]),
+                   "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                   : "memory");
+    }
+    __syncwarp();
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + tc));
+    if constexpr (EPI == EPI_RESID_F32) {
+      if (p.gamma != nullptr) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + tc));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = 4 * i + tr;
+      const int r = row0 + rl;
+      float4 a;
+      const uint32_t sa = stage_addr + rl * 128 + ((((lane & 7)) ^ (rl & 7)) << 4);
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(sa));
+      a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+      if constexpr (EPI == EPI_BIAS_GELU_HALF) {
+        a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
+      }
+      if (r >= p.M) continue;
+      if constexpr (EPI == EPI_BIAS_HALF || EPI == EPI_BIAS_GELU_HALF) {
+        uint2 w;
+        w.x = pack16(a.x, a.y, p.bf16);
+        w.y = pack16(a.z, a.w, p.bf16);
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + (long long)r * p.ldo + col + tc) = w;
+      } else if constexpr (EPI == EPI_RESID_F32) {
+        a.x = fmaf(g4.x, a.x, res[i].x); a.y = fmaf(g4.y, a.y, res[i].y);
+        a.z = fmaf(g4.z, a.z, res[i].z); a.w = fmaf(g4.w, a.w, res[i].w);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + col + tc) = a;
+      } else if constexpr (EPI == EPI_PATCH_F32) {
+        const int img = r / p.patches, pi = r % p.patches;
+        const float4 p4 = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)(1 + pi) * p.N + col + tc));
+        a.x += p4.x; a.y += p4.y; a.z += p4.z; a.w += p4.w;
+        const long long orow = (long long)img * (p.patches + 1) + 1 + pi;
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col + tc) = a;
+      } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + col + tc) = a;
+      }
+    }
+    __syncwarp();  // staging tile is rewritten by the next chunk
+  }
+}
+
+// ============================================================================================================
+// single-CTA tiles
+// ============================================================================================================
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;       // 32 KB @ BN=256
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256: power of two
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kEpiSmemBytes + BAR_BYTES + 1024;  // +1024: alignment
+};
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const KParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* smem_epi = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiSmemBytes);
   uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + C::STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * C::STAGES;   // [2]       MMA -> epilogue
@@ -82,7 +185,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
@@ -120,7 +222,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_wait(&empty_bar[s], ph ^ 1, 1);
           mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
           tma_load_2d(&tmap_a, &full_bar[s], smem_a + s * C::A_BYTES, kb * BLOCK_K, m_blk * BLOCK_M);
           tma_load_2d(&tmap_b, &full_bar[s], smem_b + s * C::B_BYTES, kb * BLOCK_K, n_blk * BN);
@@ -137,11 +239,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int as = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aph ^ 1);  // epilogue has drained this accumulator
+        mbar_wait(&tempty_bar[as], aph ^ 1, 2);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[s], ph);
+          mbar_wait(&full_bar[s], ph, 3);
           tc_fence_after();
           const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + s * C::A_BYTES));
           const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + s * C::B_BYTES));
@@ -158,96 +260,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else if (warp >= kFirstEpiWarp) {
     // ===================== epilogue =====================
-    const int q = warp & 3;                      // TMEM lane quadrant this warp may access
-    const int half = (warp - kFirstEpiWarp) >> 2;  // which half of the BN columns
-    constexpr int COLS_PER_WARP = BN / 2;
+    const int q = warp & 3;                         // TMEM lane quadrant this warp may access
+    const int half = (warp - kFirstEpiWarp) >> 2;   // which half of the BN columns
+    uint8_t* stage = smem_epi + (warp - kFirstEpiWarp) * kStageTileBytes;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
-      mbar_wait(&tfull_bar[as], aph);
+      mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      long long out_row = row;
-      const float* pos_row = nullptr;
-      if constexpr (EPI == EPI_PATCH_F32) {
-        const int img = row / p.patches, pi = row % p.patches;
-        out_row = (long long)img * (p.patches + 1) + 1 + pi;
-        pos_row = p.pos + (long long)(1 + pi) * p.N;
-      }
-#pragma unroll 1
-      for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
-        const int col_in_tile = half * COLS_PER_WARP + c0;
-        const int col = n_blk * BN + col_in_tile;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN + col_in_tile), v);
-        tmem_ld_wait();
-        if (col >= p.N) continue;  // warp-uniform (N is a multiple of 32 for every layer on the path)
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
-            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-          }
-        }
-        if constexpr (EPI == EPI_BIAS_GELU_HALF) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-        }
-        if constexpr (EPI == EPI_BIAS_HALF || EPI == EPI_BIAS_GELU_HALF) {
-          if (row_ok) {
-            uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + out_row * p.ldo + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 w;
-              w.x = pack16(f[j], f[j + 1], p.bf16);
-              w.y = pack16(f[j + 2], f[j + 3], p.bf16);
-              w.z = pack16(f[j + 4], f[j + 5], p.bf16);
-              w.w = pack16(f[j + 6], f[j + 7], p.bf16);
-              *reinterpret_cast<uint4*>(o + j) = w;
-            }
-          }
-        } else {
-          if constexpr (EPI == EPI_RESID_F32) {
-            if (p.gamma != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + j));
-                f[j] *= g4.x; f[j + 1] *= g4.y; f[j + 2] *= g4.z; f[j + 3] *= g4.w;
-              }
-            }
-            if (row_ok) {
-              const float* r = p.resid + (long long)row * p.ldr + col;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 r4 = *reinterpret_cast<const float4*>(r + j);
-                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-              }
-            }
-          }
-          if constexpr (EPI == EPI_PATCH_F32) {
-            if (row_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 p4 = __ldg(reinterpret_cast<const float4*>(pos_row + col + j));
-                f[j] += p4.x; f[j + 1] += p4.y; f[j + 2] += p4.z; f[j + 3] += p4.w;
-              }
-            }
-          }
-          if (row_ok) {
-            float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          }
-        }
-      }
-      // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
+      epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * BLOCK_M + q * 32, n_blk * BN, half * (BN / 2),
+                         (half + 1) * (BN / 2), stage);
+      // all TMEM reads of this accumulator are complete (wait::ld): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -262,24 +287,169 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
 }
 
+// ============================================================================================================
+// CTA-pair tiles (cta_group::2): 256 x 256 output tile per cluster of two CTAs
+// ============================================================================================================
+struct Cfg2 {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;    // this CTA's 128 rows of A: 16 KB
+  static constexpr int B_BYTES = (BN / 2) * BLOCK_K * 2;   // this CTA's 128 rows of W: 16 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB per CTA per stage
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kEpiSmemBytes + BAR_BYTES + 1024;
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const KParams p) {
+  using C = Cfg2;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
+  uint8_t* smem_epi = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiSmemBytes);
+  uint64_t* full_bar = bars;                   // [STAGES] used in the leader CTA: bytes of BOTH CTAs land here
+  uint64_t* empty_bar = bars + C::STAGES;      // [STAGES] per CTA, signalled by the leader's multicast commit
+  uint64_t* tfull_bar = bars + 2 * C::STAGES;  // [2]      per CTA, multicast commit
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2]      used in the leader: epilogue warps of both CTAs arrive
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = p.K / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * kNumEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_cg2(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; bytes are credited to the leader's full barrier) ========
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int m0 = m_blk * 2 * BLOCK_M + rank * BLOCK_M;
+        const int n0 = n_blk * BN + rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1, 11);
+          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[s]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+          tma_load_2d_cg2(&tmap_a, leader_full, smem_a + s * C::A_BYTES, kb * BLOCK_K, m0);
+          tma_load_2d_cg2(&tmap_b, leader_full, smem_b + s * C::B_BYTES, kb * BLOCK_K, n0);
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int lt = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++lt) {
+        const int as = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1, 12);  // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph, 13);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + s * C::A_BYTES));
+          const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + s * C::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_cg2_mc(&empty_bar[s], 0b11);  // free the slot in both CTAs
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit_cg2_mc(&tfull_bar[as], 0b11);   // accumulator halves complete in both CTAs
+      }
+    }
+  } else if (warp >= kFirstEpiWarp) {
+    // ===================== epilogue (each CTA drains its own 128 rows) =====================
+    const int q = warp & 3;
+    const int half = (warp - kFirstEpiWarp) >> 2;
+    uint8_t* stage = smem_epi + (warp - kFirstEpiWarp) * kStageTileBytes;
+    int lt = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++lt) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int as = lt & 1;
+      const uint32_t aph = (lt >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aph, 14);
+      tc_fence_after();
+      epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * 2 * BLOCK_M + rank * BLOCK_M + q * 32, n_blk * BN,
+                         half * (BN / 2), (half + 1) * (BN / 2), stage);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still signal it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ============================================================================================================
+// host side
+// ============================================================================================================
+KParams make_params(const GemmArgs& a, int umma_m, int umma_n) {
+  KParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.bias = a.bias; p.gamma = a.gamma; p.resid = a.resid; p.ldr = a.ldr;
+  p.out = a.out; p.ldo = a.ldo; p.pos = a.pos; p.patches = a.patches;
+  p.idesc = make_idesc(a.bf16 ? kFmtBF16 : kFmtF16, umma_m, umma_n);
+  p.bf16 = a.bf16;
+  return p;
+}
+
 template <int BN, int EPI>
 int launch_one(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    KB_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       C::SMEM_BYTES));
+    KB_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  KParams p;
-  p.M = a.M; p.N = a.N; p.K = a.K;
-  p.bias = a.bias; p.gamma = a.gamma; p.resid = a.resid; p.ldr = a.ldr;
-  p.out = a.out; p.ldo = a.ldo; p.pos = a.pos; p.patches = a.patches;
-  p.idesc = make_idesc(a.bf16 ? kFmtBF16 : kFmtF16, BLOCK_M, BN);
-  p.bf16 = a.bf16;
-  const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
-  const int n_tiles = (a.N + BN - 1) / BN;
-  const int tiles = m_tiles * n_tiles;
+  const KParams p = make_params(a, BLOCK_M, BN);
+  const int tiles = ((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BN - 1) / BN);
   int grid = num_sms();
   if (tiles < grid) grid = tiles;
   profile_gemm_begin(stream);
@@ -290,16 +460,57 @@ int launch_one(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, 
   return KB_OK;
 }
 
-template <int BN>
-int dispatch_epi(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
-  switch (a.epi) {
-    case EPI_BIAS_HALF: return launch_one<BN, EPI_BIAS_HALF>(a, ta, tb, stream);
-    case EPI_BIAS_GELU_HALF: return launch_one<BN, EPI_BIAS_GELU_HALF>(a, ta, tb, stream);
-    case EPI_RESID_F32: return launch_one<BN, EPI_RESID_F32>(a, ta, tb, stream);
-    case EPI_BIAS_F32: return launch_one<BN, EPI_BIAS_F32>(a, ta, tb, stream);
-    case EPI_PATCH_F32: return launch_one<BN, EPI_PATCH_F32>(a, ta, tb, stream);
-    default: return set_error(KB_ERR_ARG, "gemm: unknown epilogue %d", a.epi);
+template <int EPI>
+int launch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+  using C = Cfg2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    KB_CUDA_CHECK(cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
   }
+  const KParams p = make_params(a, 2 * BLOCK_M, C::BN);
+  const int tiles = ((a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((a.N + C::BN - 1) / C::BN);
+  int pairs = num_sms() / 2;
+  if (tiles < pairs) pairs = tiles;
+  profile_gemm_begin(stream);
+  gemm2_kernel<EPI><<<2 * pairs, kThreads, C::SMEM_BYTES, stream>>>(ta, tb, p);  // cluster dims are compile-time (2,1,1)
+  profile_gemm_end(stream, 2.0 * a.M * a.N * a.K);
+  note_launch();
+  KB_CUDA_CHECK(cudaGetLastError());
+  return KB_OK;
+}
+
+#define KB_DISPATCH_EPI(FN, ...)                                                             \
+  switch (a.epi) {                                                                           \
+    case EPI_BIAS_HALF: return FN<__VA_ARGS__ EPI_BIAS_HALF>(a, ta, tb, stream);             \
+    case EPI_BIAS_GELU_HALF: return FN<__VA_ARGS__ EPI_BIAS_GELU_HALF>(a, ta, tb, stream);   \
+    case EPI_RESID_F32: return FN<__VA_ARGS__ EPI_RESID_F32>(a, ta, tb, stream);             \
+    case EPI_BIAS_F32: return FN<__VA_ARGS__ EPI_BIAS_F32>(a, ta, tb, stream);               \
+    case EPI_PATCH_F32: return FN<__VA_ARGS__ EPI_PATCH_F32>(a, ta, tb, stream);             \
+    default: return set_error(KB_ERR_ARG, "gemm: unknown epilogue %d", a.epi);               \
+  }
+
+int dispatch_256(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+  KB_DISPATCH_EPI(launch_one, 256, )
+}
+int dispatch_128(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+  KB_DISPATCH_EPI(launch_one, 128, )
+}
+int dispatch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+  KB_DISPATCH_EPI(launch_pair, )
+}
+
+// KEEPB200_GEMM = auto (default) | pair | wide | narrow : force one main-loop variant (A/B measurements)
+int forced_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = std::getenv("KEEPB200_GEMM");
+    mode = 0;
+    if (e && !std::strcmp(e, "pair")) mode = 1;
+    if (e && !std::strcmp(e, "wide")) mode = 2;
+    if (e && !std::strcmp(e, "narrow")) mode = 3;
+  }
+  return mode;
 }
 
 }  // namespace
@@ -311,17 +522,20 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.epi == EPI_RESID_F32 && a.resid == nullptr) return set_error(KB_ERR_ARG, "gemm: residual epilogue without resid");
   if (a.epi == EPI_PATCH_F32 && (a.pos == nullptr || a.patches <= 0))
     return set_error(KB_ERR_ARG, "gemm: patch epilogue without pos/patches");
-  // Tile-width choice: 256-wide tiles halve the A re-reads; 128-wide tiles give twice as many work units
-  // when the problem is too small to fill the machine.
-  const int m_tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
-  const bool wide = (a.N % 256 == 0) && ((long long)m_tiles * (a.N / 256) >= num_sms());
+  // Variant choice: CTA-pair 256x256 tiles when they fill the machine; otherwise 128-row tiles, 256 wide when
+  // that still gives every SM a tile, else 128 wide (twice as many work units for small problems).
+  const long long m128 = (a.M + BLOCK_M - 1) / BLOCK_M, m256 = (a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const bool n256 = (a.N % 256 == 0);
+  int mode = forced_mode();
+  if (mode == 0) mode = (n256 && m256 * (a.N / 256) >= num_sms() / 2) ? 1 : (n256 && m128 * (a.N / 256) >= num_sms()) ? 2 : 3;
+  if ((mode == 1 || mode == 2) && !n256) mode = 3;
   const int dt = a.bf16 ? KB_BF16 : KB_F16;
   CUtensorMap ta, tb;
   int rc = get_tmap_2d(a.A, dt, a.M, a.K, a.lda, BLOCK_M, &ta);
   if (rc) return rc;
-  rc = get_tmap_2d(a.W, dt, a.N, a.K, a.ldw, wide ? 256 : 128, &tb);
+  rc = get_tmap_2d(a.W, dt, a.N, a.K, a.ldw, mode == 2 ? 256 : 128, &tb);
   if (rc) return rc;
-  return wide ? dispatch_epi<256>(a, ta, tb, stream) : dispatch_epi<128>(a, ta, tb, stream);
+  return mode == 1 ? dispatch_pair(a, ta, tb, stream) : mode == 2 ? dispatch_256(a, ta, tb, stream) : dispatch_128(a, ta, tb, stream);
 }
 
 }  // namespace kb
