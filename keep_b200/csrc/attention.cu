@@ -15,6 +15,9 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace kb {
 namespace {
 
@@ -227,6 +230,12 @@ attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, i
 int launch_attention(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
                      int64_t mask_stride, float scale, cudaStream_t stream) {
   if (B <= 0 || S <= 0 || H <= 0) return KB_OK;
+  static int force_v1 = -1;
+  if (force_v1 < 0) {
+    const char* e = std::getenv("KEEPB200_ATTN");
+    force_v1 = (e && !std::strcmp(e, "v1")) ? 1 : 0;
+  }
+  if (attention_tc_supports(S) && !force_v1) return launch_attention_tc(qkv, out, B, S, H, bf16, key_mask, mask_stride, scale, stream);
   if (S > 512) return set_error(KB_ERR_ARG, "attention: S=%d > 512 unsupported", S);
   const int spad = (S + KB_ - 1) / KB_ * KB_;
   const int smem = (2 * spad + QB) * 128 + spad * 4;

@@ -1,0 +1,398 @@
+// tcgen05 attention for sequences of 65..224 tokens (ViT: 197; longer BERT prompts), head dim 64:
+//     out = softmax(Q K^T * scale + key_mask) V      per (batch, head)
+//
+// One persistent CTA per SM; everything between the two MMAs stays on-chip (FlashAttention-4 style roles):
+//   * unit of work = 128 query rows of one (batch, head). The keys of a head fit ONE tile (S_pad <= 224), so the
+//     whole score row is available: exact two-pass softmax, no online rescaling;
+//   * warp 0      : TMA producer. Q tile(s) + K go through a 2-slot ring, V through a 3-slot ring (Q/K are dead as
+//                   soon as the S MMAs of the head are done, V only after its last PV MMA), all read straight out of
+//                   the fused q|k|v projection buffer [B*S, 3*H*64] with SWIZZLE_128B boxes;
+//   * warp 1      : MMA issuer. S = Q K^T (tcgen05.mma SS, 128 x S_pad x 16, fp32 S in TMEM region u&1), and
+//                   O = P V (tcgen05.mma TS: P is read from TMEM where it overwrote S; V is the MN-major B operand);
+//                   issue order S0 S1 | PV0 S2 | PV1 S3 | ... keeps the tensor pipe busy under the softmax;
+//   * warps 4-7 / 8-11 : two softmax groups, one per S region; a thread owns one query row: tcgen05.ld S -> row max ->
+//                   exp2 -> row sum -> 16-bit P written back over S with tcgen05.st. The exp2 pass (MUFU-bound) is
+//                   serialised between the groups with a baton so that one group's MUFU work overlaps the other
+//                   group's TMEM traffic and both MMAs;
+//   * warps 12-15 : output group: tcgen05.ld O (single 64-column accumulator), divide by the row sum, store rows.
+//
+// Reference semantics: timm Attention -> F.scaled_dot_product_attention and BertSelfAttention with
+// the additive key mask (transformers modeling_bert.py:115-140).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace kb {
+namespace {
+
+constexpr int kAtcThreads = 512;
+constexpr int kMaxSpad = 224;                 // 2 * S_pad + 64 (O) <= 512 TMEM columns
+constexpr int Q_TILE_BYTES = 128 * 128;       // 128 rows x 64 x 16-bit
+constexpr int K_TILE_BYTES = kMaxSpad * 128;  // 28 KB
+constexpr int QK_SLOT_BYTES = 2 * Q_TILE_BYTES + K_TILE_BYTES;  // 60 KB (multiple of 1024)
+constexpr int V_SLOT_BYTES = kMaxSpad * 128;  // 28 KB
+constexpr int kQkSlots = 2, kVSlots = 3;
+
+struct AtcParams {
+  int B, S, H, S_pad, n_qt;
+  int items;       // B * H
+  const long long* key_mask;
+  long long mask_stride;
+  uint16_t* out;
+  float scale_log2;
+  uint32_t idesc_s;   // 128 x S_pad, both operands K-major
+  uint32_t idesc_pv;  // 128 x 64, B (V) MN-major
+  int bf16;
+};
+
+struct Smem {  // offsets inside the 1024-aligned dynamic smem block
+  static constexpr int qk = 0;
+  static constexpr int v = kQkSlots * QK_SLOT_BYTES;
+  static constexpr int bias = v + kVSlots * V_SLOT_BYTES;   // [kVSlots][256] float: 0 / -inf per key
+  static constexpr int meta = bias + kVSlots * 256 * 4;     // [kVSlots] int: index of the first masked key
+  static constexpr int rowsum = meta + 64;                  // [2 regions][2 parities][128] float
+  static constexpr int bars = rowsum + 2 * 2 * 128 * 4;
+  static constexpr int total = bars + 256;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack16(float a, float b, int bf16) {
+  if (bf16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kAtcThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                    const AtcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_bias = reinterpret_cast<float*>(smem + Smem::bias);
+  int* s_meta = reinterpret_cast<int*>(smem + Smem::meta);
+  float* s_rowsum = reinterpret_cast<float*>(smem + Smem::rowsum);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+  uint64_t* qk_full = bars;        // [2] TMA -> MMA
+  uint64_t* qk_empty = bars + 2;   // [2] MMA (last S of the head committed) -> TMA
+  uint64_t* v_full = bars + 4;     // [3] TMA + key-bias writer -> MMA, softmax
+  uint64_t* v_empty = bars + 7;    // [3] MMA (last PV of the head committed) -> TMA
+  uint64_t* s_ready = bars + 10;   // [2] MMA -> softmax group
+  uint64_t* p_ready = bars + 12;   // [2] softmax group -> MMA, output group
+  uint64_t* o_ready = bars + 14;   // [1] MMA -> output group
+  uint64_t* o_free = bars + 15;    // [1] output group -> MMA
+  uint64_t* turn = bars + 16;      // [2] exp2-pass baton between the softmax groups
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_my = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // heads of this CTA
+  const int U = n_my * p.n_qt;                                                          // units of this CTA
+  const uint32_t o_col = 2 * p.S_pad;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_kv);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qk_full[i], 1);
+      mbar_init(&qk_empty[i], 1);
+      mbar_init(&s_ready[i], 1);
+      mbar_init(&p_ready[i], 4);  // one elected lane per softmax warp
+      mbar_init(&turn[i], 4);
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&v_full[i], 2);   // expect_tx arrive + bias-written arrive
+      mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(o_ready, 1);
+    mbar_init(o_free, 4);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int kv_bytes = p.S_pad * 128;
+
+  if (warp == 0) {
+    // ===================== producer: TMA tiles + key bias =====================
+    for (int j = 0; j < n_my; ++j) {
+      const int item = blockIdx.x + j * gridDim.x;
+      const int b = item / p.H, h = item % p.H;
+      const int row0 = b * p.S;
+      const int qs = j & 1, vs = j % 3;
+      if (lane == 0) {
+        mbar_wait(&qk_empty[qs], ((j >> 1) & 1) ^ 1, 21);
+        uint8_t* base = smem + Smem::qk + qs * QK_SLOT_BYTES;
+        mbar_arrive_expect_tx(&qk_full[qs], p.n_qt * Q_TILE_BYTES + kv_bytes);
+        for (int t = 0; t < p.n_qt; ++t)
+          tma_load_2d(&tmap_q, &qk_full[qs], base + t * Q_TILE_BYTES, h * 64, row0 + t * 128);
+        tma_load_2d(&tmap_kv, &qk_full[qs], base + 2 * Q_TILE_BYTES, (p.H + h) * 64, row0);
+        mbar_wait(&v_empty[vs], ((j / 3) & 1) ^ 1, 22);
+        mbar_arrive_expect_tx(&v_full[vs], kv_bytes);
+        tma_load_2d(&tmap_kv, &v_full[vs], smem + Smem::v + vs * V_SLOT_BYTES, (2 * p.H + h) * 64, row0);
+      }
+      __syncwarp();
+      // additive key bias: 0 for attended keys, -inf for masked keys and the padding up to S_pad
+      int first_bad = p.S_pad;
+      for (int k = lane; k < p.S_pad; k += 32) {
+        bool ok = k < p.S;
+        if (ok && p.key_mask != nullptr) ok = p.key_mask[(long long)b * p.mask_stride + k] != 0;
+        s_bias[vs * 256 + k] = ok ? 0.f : -INFINITY;
+        if (!ok && k < first_bad) first_bad = k;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
+      if (lane == 0) s_meta[vs] = first_bad;  // 32-key chunks entirely below it need no bias at all
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&v_full[vs]);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      auto issue_s = [&](int u) {
+        const int j = u / p.n_qt, t = u % p.n_qt, qs = j & 1, r = u & 1;
+        if (t == 0) mbar_wait(&qk_full[qs], (j >> 1) & 1, 23);
+        tc_fence_after();
+        // region r is free: PV(u-2) was issued before this in program order (the tensor pipe executes in order) and
+        // softmax(u-2) finished reading S before p_ready(u-2), which PV(u-2) waited for
+        const uint8_t* base = smem + Smem::qk + qs * QK_SLOT_BYTES;
+        const uint64_t dq = make_smem_desc_sw128(smem_u32(base + t * Q_TILE_BYTES));
+        const uint64_t dk = make_smem_desc_sw128(smem_u32(base + 2 * Q_TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // head dim 64 = 4 x 16
+          umma_f16_ss(tmem_base + r * p.S_pad, dq + 2 * k, dk + 2 * k, p.idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_ready[r]);
+        if (t == p.n_qt - 1) umma_commit(&qk_empty[qs]);  // Q/K of this head are dead once these MMAs complete
+      };
+      auto issue_pv = [&](int u) {
+        const int j = u / p.n_qt, t = u % p.n_qt, vs = j % 3, r = u & 1;
+        mbar_wait(&p_ready[r], (u >> 1) & 1, 24);
+        if (t == 0) mbar_wait(&v_full[vs], (j / 3) & 1, 25);
+        if (u > 0) mbar_wait(o_free, (u - 1) & 1, 26);  // the output group has drained O of the previous unit
+        tc_fence_after();
+        const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + Smem::v + vs * V_SLOT_BYTES));
+        const int ksteps = p.S_pad / 16;
+        for (int k = 0; k < ksteps; ++k)  // 16 keys per MMA: P advances 8 TMEM columns, V advances 16 rows = 2048 B
+          umma_f16_ts(tmem_base + o_col, tmem_base + r * p.S_pad + 8 * k, dv + 128 * k, p.idesc_pv, k != 0 ? 1u : 0u);
+        umma_commit(o_ready);
+        if (t == p.n_qt - 1) umma_commit(&v_empty[vs]);
+      };
+      if (U > 0) issue_s(0);
+      if (U > 1) issue_s(1);
+      for (int u = 0; u < U; ++u) {
+        issue_pv(u);
+        if (u + 2 < U) issue_s(u + 2);
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ===================== softmax groups =====================
+    const int g = (warp - 4) >> 2;   // group = S region
+    const int q = warp & 3;          // TMEM lane quadrant
+    const uint32_t t_row = tmem_base + g * p.S_pad + (uint32_t(q * 32) << 16);
+    const int row_in_tile = q * 32 + lane;
+    for (int u = g; u < U; u += 2) {
+      const int j = u / p.n_qt, vs = j % 3;
+      const int n = u >> 1;
+      mbar_wait(&v_full[vs], (j / 3) & 1, 27);  // key bias / meta visible
+      const float* bias = s_bias + vs * 256;
+      // warps whose 32 query rows all lie beyond S (tail of the last tile) skip the TMEM traffic: their P rows
+      // stay whatever they were, the corresponding O rows are never stored
+      const bool live = (u % p.n_qt) * 128 + q * 32 < p.S;
+      const int fast_end = live ? (s_meta[vs] & ~31) : 0;    // keys [0, fast_end) are all attended: no bias needed
+      const int slow_end = live ? p.S_pad : 0;
+      mbar_wait(&s_ready[g], n & 1, 28);
+      tc_fence_after();
+      // ---- pass 1: row max of scale*s + bias (scale > 0, so the raw max is taken where there is no bias) ----
+      float mx_raw = -INFINITY, mx = -INFINITY;
+      uint32_t va[32], vb[32];
+      if (fast_end > 0) tmem_ld_32x32(t_row, va);
+      for (int c = 0; c < fast_end; c += 64) {  // software-pipelined: the next chunk is in flight while this one is reduced
+        tmem_ld_wait_dep(va);
+        if (c + 32 < fast_end) tmem_ld_32x32(t_row + c + 32, vb);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, __uint_as_float(va[i]));
+        if (c + 32 < fast_end) {
+          tmem_ld_wait_dep(vb);
+          if (c + 64 < fast_end) tmem_ld_32x32(t_row + c + 64, va);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, __uint_as_float(vb[i]));
+        }
+      }
+      for (int c = fast_end; c < slow_end; c += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_row + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + c + i);
+          mx = fmaxf(mx, fmaf(__uint_as_float(v[i]), p.scale_log2, b4.x));
+          mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 1]), p.scale_log2, b4.y));
+          mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 2]), p.scale_log2, b4.z));
+          mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 3]), p.scale_log2, b4.w));
+        }
+      }
+      mx = fmaxf(mx, mx_raw * p.scale_log2);
+      if (mx == -INFINITY) mx = 0.f;  // fully masked row: avoid (-inf) - (-inf)
+      const float neg_mx = -mx;
+      // ---- pass 2: p = exp2(scale*s + bias - max), row sum, P (16-bit) written over S ----
+      // baton: wait until the other group has finished its exp2 pass (group 0's first unit goes first)
+      if (g == 1) mbar_wait(&turn[1], n & 1, 29);
+      else if (n > 0) mbar_wait(&turn[0], (n - 1) & 1, 30);
+      float sum = 0.f;
+      auto exp_chunk = [&](const uint32_t (&v)[32], int c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float e0 = ex2f(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_mx));
+          const float e1 = ex2f(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_mx));
+          sum += e0 + e1;
+          pk[i] = pack16(e0, e1, p.bf16);
+        }
+        tmem_st_32x16(t_row + (c >> 1), pk);
+      };
+      if (fast_end > 0) tmem_ld_32x32(t_row, va);
+      for (int c = 0; c < fast_end; c += 64) {
+        tmem_ld_wait_dep(va);
+        if (c + 32 < fast_end) tmem_ld_32x32(t_row + c + 32, vb);
+        exp_chunk(va, c);
+        if (c + 32 < fast_end) {
+          tmem_ld_wait_dep(vb);
+          if (c + 64 < fast_end) tmem_ld_32x32(t_row + c + 64, va);
+          exp_chunk(vb, c + 32);
+        }
+      }
+      for (int c = fast_end; c < slow_end; c += 16) {
+        uint32_t v[16];
+        tmem_ld_32x16(t_row + c, v);
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + c + 2 * i);
+          const float e0 = ex2f(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, b4.x + neg_mx));
+          const float e1 = ex2f(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, b4.y + neg_mx));
+          const float e2 = ex2f(fmaf(__uint_as_float(v[2 * i + 2]), p.scale_log2, b4.z + neg_mx));
+          const float e3 = ex2f(fmaf(__uint_as_float(v[2 * i + 3]), p.scale_log2, b4.w + neg_mx));
+          sum += (e0 + e1) + (e2 + e3);
+          pk[i] = pack16(e0, e1, p.bf16);
+          pk[i + 1] = pack16(e2, e3, p.bf16);
+        }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(t_row + (c >> 1)),
+                     "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                     : "memory");
+      }
+      s_rowsum[(g * 2 + (n & 1)) * 128 + row_in_tile] = sum;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&turn[g ^ 1]);  // the other group may start its exp2 pass
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[g]);
+    }
+  } else if (warp >= 12) {
+    // ===================== output group: O / row sum -> context rows =====================
+    const int q = warp & 3;
+    const uint32_t t_o = tmem_base + o_col + (uint32_t(q * 32) << 16);
+    const int row_in_tile = q * 32 + lane;
+    for (int u = 0; u < U; ++u) {
+      const int j = u / p.n_qt, t = u % p.n_qt, r = u & 1, n = u >> 1;
+      const int item = blockIdx.x + j * gridDim.x;
+      const int b = item / p.H, h = item % p.H;
+      mbar_wait(&p_ready[r], n & 1, 31);  // row sums of this unit are visible
+      const float sum = s_rowsum[(r * 2 + (n & 1)) * 128 + row_in_tile];
+      mbar_wait(o_ready, u & 1, 32);
+      tc_fence_after();
+      uint32_t va[32], vb[32];
+      if (t * 128 + q * 32 < p.S) {  // warp-uniform: skip the tail warps of the last tile
+        tmem_ld_32x32(t_o, va);
+        tmem_ld_32x32(t_o + 32, vb);
+        tmem_ld_wait_dep(va);
+        tmem_ld_wait_dep(vb);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);  // O may be overwritten by the next PV
+      const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+      const int srow = t * 128 + row_in_tile;
+      if (srow < p.S) {
+        uint16_t* orow = p.out + ((long long)b * p.S + srow) * ((long long)p.H * 64) + h * 64;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          w.x = pack16(__uint_as_float(va[i]) * inv, __uint_as_float(va[i + 1]) * inv, p.bf16);
+          w.y = pack16(__uint_as_float(va[i + 2]) * inv, __uint_as_float(va[i + 3]) * inv, p.bf16);
+          w.z = pack16(__uint_as_float(va[i + 4]) * inv, __uint_as_float(va[i + 5]) * inv, p.bf16);
+          w.w = pack16(__uint_as_float(va[i + 6]) * inv, __uint_as_float(va[i + 7]) * inv, p.bf16);
+          *reinterpret_cast<uint4*>(orow + i) = w;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          w.x = pack16(__uint_as_float(vb[i]) * inv, __uint_as_float(vb[i + 1]) * inv, p.bf16);
+          w.y = pack16(__uint_as_float(vb[i + 2]) * inv, __uint_as_float(vb[i + 3]) * inv, p.bf16);
+          w.z = pack16(__uint_as_float(vb[i + 4]) * inv, __uint_as_float(vb[i + 5]) * inv, p.bf16);
+          w.w = pack16(__uint_as_float(vb[i + 6]) * inv, __uint_as_float(vb[i + 7]) * inv, p.bf16);
+          *reinterpret_cast<uint4*>(orow + 32 + i) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+bool attention_tc_supports(int S) { return S > 64 && (S + 15) / 16 * 16 <= kMaxSpad; }
+
+int launch_attention_tc(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
+                        int64_t mask_stride, float scale, cudaStream_t stream) {
+  const int S_pad = (S + 15) / 16 * 16;
+  if (S_pad > kMaxSpad) return set_error(KB_ERR_ARG, "attention_tc: S=%d > %d", S, kMaxSpad);
+  const int dt = bf16 ? KB_BF16 : KB_F16;
+  const int64_t rows = (int64_t)B * S, cols = 3LL * H * 64;
+  CUtensorMap tq, tkv;
+  int rc = get_tmap_2d(qkv, dt, rows, cols, cols, 128, &tq);
+  if (rc) return rc;
+  rc = get_tmap_2d(qkv, dt, rows, cols, cols, S_pad, &tkv);
+  if (rc) return rc;
+  static bool attr_set = false;
+  const int smem = Smem::total + 1024;
+  if (!attr_set) {
+    KB_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  AtcParams p;
+  p.B = B; p.S = S; p.H = H; p.S_pad = S_pad; p.n_qt = (S + 127) / 128; p.items = B * H;
+  p.key_mask = reinterpret_cast<const long long*>(key_mask);
+  p.mask_stride = mask_stride;
+  p.out = static_cast<uint16_t*>(out);
+  p.scale_log2 = scale * 1.4426950408889634f;
+  const uint32_t fmt = bf16 ? kFmtBF16 : kFmtF16;
+  p.idesc_s = make_idesc(fmt, 128, S_pad, 0, 0);
+  p.idesc_pv = make_idesc(fmt, 128, 64, 0, 1);  // B operand (V) is MN-major: rows are keys, 64 head-dim values contiguous
+  p.bf16 = bf16;
+  int grid = num_sms();
+  if (p.items < grid) grid = p.items;
+  attention_tc_kernel<<<grid, kAtcThreads, smem, stream>>>(tq, tkv, p);
+  note_launch();
+  KB_CUDA_CHECK(cudaGetLastError());
+  return KB_OK;
+}
+
+}  // namespace kb

@@ -80,6 +80,11 @@ int launch_act_l2norm(const float* x, int64_t rows, int D, int act, float* y, cu
 int launch_attention(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
                      int64_t mask_stride, float scale, cudaStream_t stream);
 
+// tcgen05 variant (64 < S <= 224); launch_attention dispatches to it unless KEEPB200_ATTN=v1
+bool attention_tc_supports(int S);
+int launch_attention_tc(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
+                        int64_t mask_stride, float scale, cudaStream_t stream);
+
 // ---- ViT front end ----------------------------------------------------------------------------------------
 // tiles fp32 NCHW [B,3,G*16,G*16] -> patches16 [B*G*G, 768] (col = c*256+ky*16+kx); also writes the CLS
 // rows x[b*(G*G+1), :] = cls + pos[0].

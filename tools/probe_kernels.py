@@ -157,6 +157,27 @@ def probe_attention():
     run("att-bf16", lambda: case(2, 197, 16, False, torch.bfloat16))
 
 
+def bench_attention():
+    for (B, S, H, masked) in [(512, 197, 16, False), (2048, 32, 12, True)]:
+        qkv = torch.randn(B * S, 3 * H * 64, device=dev).half()
+        mask = None
+        if masked:
+            lens = torch.randint(4, S + 1, (B,))
+            mask = (torch.arange(S)[None, :] < lens[:, None]).long().to(dev)
+        for _ in range(3):
+            ops.attention(qkv, B, S, H, key_mask=mask)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.attention(qkv, B, S, H, key_mask=mask)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        fl = 4.0 * B * H * S * S * 64
+        print(f"[perf] attention B={B} S={S} H={H} mask={int(masked)}: {ms:.3f} ms = {fl / ms / 1e9:.0f} TFLOP/s", flush=True)
+
+
 def probe_sim():
     def sim():
         feats = torch.randn(1000, 768, device=dev) * 2
@@ -254,6 +275,8 @@ if __name__ == "__main__":
         probe_sim()
     if "perf" in which and all(ok for n, ok in RESULTS if n.startswith("gemm")):
         run("perf", bench_gemm)
+    if "attperf" in which:
+        run("attperf", bench_attention)
     nfail = sum(1 for _, ok in RESULTS if not ok)
     print(f"SUMMARY: {len(RESULTS) - nfail}/{len(RESULTS)} ok")
     sys.exit(1 if nfail else 0)
