@@ -242,6 +242,13 @@ def main():
     ms_total = timed(step_resident, args.steps)
     gemm_ms, gemm_flops, gemm_n, all_n = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
     _lib.check(L.keepb200_profile_end(C.byref(gemm_ms), C.byref(gemm_flops), C.byref(gemm_n), C.byref(all_n)), "profile_end")
+    gemm_table = []
+    for rec in (L.keepb200_profile_table() or b"").decode().split(";"):
+        if rec:
+            M_, N_, K_, epi_, n_, ms_, tf_ = rec.split(",")
+            gemm_table.append({"M": int(M_), "N": int(N_), "K": int(K_), "epi": int(epi_), "launches": int(n_),
+                               "ms": float(ms_), "tflops": float(tf_)})
+    gemm_table.sort(key=lambda r: -r["ms"])
     clocks = sampler.stop() if sampler else None
     ms_step = ms_total / args.steps
     value = world * n_tiles / (ms_step / 1e3)
@@ -314,7 +321,7 @@ def main():
                          "frac": (ach / peaks["tflops_sustained"]) if ach else None, "traffic": traffic,
                          "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                          "gemm_share_of_step": gemm_ms.value / ms_total if ms_total else None,
-                         "gemm_launches": gemm_n.value,
+                         "gemm_launches": gemm_n.value, "per_shape": gemm_table[:6],
                          "whole_path_frac": value * FLOP_PER_TILE / (world * peaks["tflops_sustained"] * 1e12)},
             "e2e": e2e, "gpu_launches": int(all_n.value), "clocks": clocks,
         }

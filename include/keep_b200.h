@@ -149,6 +149,8 @@ int64_t keepb200_launch_count(void);
  * (2*M*N*K per launch) of those launches, their count, and the count of ALL kernels launched in between. */
 int keepb200_profile_begin(void);
 int keepb200_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches, int64_t* all_launches);
+/* Per-shape summary of the last profile_end(): "M,N,K,epi,launches,ms,TFLOP/s;" records (host string). */
+const char* keepb200_profile_table(void);
 
 /* ---- single-kernel entry points (unit tests and profiling) ------------------------------------------- */
 /* out = epilogue(A[M,K] . W[N,K]^T); epi: 0 bias->16-bit, 1 bias+GELU(erf)->16-bit,

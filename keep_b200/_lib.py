@@ -66,6 +66,7 @@ SIGNATURES = {
     "keepb200_launch_count": (_i64, []),
     "keepb200_profile_begin": (_int, []),
     "keepb200_profile_end": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64)]),
+    "keepb200_profile_table": (C.c_char_p, []),
     "keepb200_op_gemm": (_int, [_p, _i64, _p, _i64, _int, _int, _int, _int, _int, _p, _p, _p, _i64, _p, _i64, _p, _int, _p]),
     "keepb200_op_layernorm": (_int, [_p, _i64, _i64, _int, _p, _p, _f, _p, _int, _p, _p]),
     "keepb200_op_attention": (_int, [_p, _p, _int, _int, _int, _int, _p, _i64, _f, _p]),

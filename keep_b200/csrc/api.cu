@@ -559,6 +559,7 @@ int keepb200_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_laun
   return rc;
 }
 int64_t keepb200_launch_count(void) { return launch_count(); }
+const char* keepb200_profile_table(void) { return profile_table(); }
 
 // ---- single-kernel entry points -----------------------------------------------------------------------------------
 int keepb200_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epi, int bf16,

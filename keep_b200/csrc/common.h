@@ -35,6 +35,8 @@ long long launch_count();
 bool profiling();
 void profile_gemm_begin(cudaStream_t s);
 void profile_gemm_end(cudaStream_t s, double flops);
+void profile_gemm_tag(int M, int N, int K, int epi);  // call right before profile_gemm_begin
+const char* profile_table();                          // per-shape summary of the last profile_end()
 int profile_begin();
 int profile_end(double* gemm_ms, double* gemm_flops, long long* gemm_launches, long long* all_launches);
 

@@ -5,7 +5,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <string>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -42,6 +45,9 @@ static std::vector<cudaEvent_t> g_ev_pool;  // pairs: [2i] start, [2i+1] stop
 static size_t g_ev_used = 0;
 static double g_prof_flops = 0.0;
 static long long g_prof_launch_base = 0;
+struct ProfTag { int M, N, K, epi; double flops; };
+static std::vector<ProfTag> g_prof_tags;  // one per GEMM event pair
+static std::string g_prof_table;
 
 void note_launch(int n) { g_launches += n; }
 long long launch_count() { return g_launches; }
@@ -63,22 +69,44 @@ void profile_gemm_end(cudaStream_t s, double flops) {
   cudaEventRecord(g_ev_pool[g_ev_used + 1], s);
   g_ev_used += 2;
   g_prof_flops += flops;
+  if (g_prof_tags.size() < g_ev_used / 2) g_prof_tags.push_back(ProfTag{0, 0, 0, -1, flops});
 }
+void profile_gemm_tag(int M, int N, int K, int epi) {
+  if (!g_prof_on) return;
+  g_prof_tags.push_back(ProfTag{M, N, K, epi, 2.0 * M * N * K});
+}
+const char* profile_table() { return g_prof_table.c_str(); }
 int profile_begin() {
   g_prof_on = true;
   g_ev_used = 0;
   g_prof_flops = 0.0;
   g_prof_launch_base = g_launches;
+  g_prof_tags.clear();
   return KB_OK;
 }
 int profile_end(double* gemm_ms, double* gemm_flops, long long* gemm_launches, long long* all_launches) {
   g_prof_on = false;
   KB_CUDA_CHECK(cudaDeviceSynchronize());
   double ms = 0.0;
+  struct Agg { long long n = 0; double ms = 0, flops = 0; };
+  std::map<std::tuple<int, int, int, int>, Agg> agg;
   for (size_t i = 0; i + 1 < g_ev_used; i += 2) {
     float t = 0.f;
     KB_CUDA_CHECK(cudaEventElapsedTime(&t, g_ev_pool[i], g_ev_pool[i + 1]));
     ms += t;
+    if (i / 2 < g_prof_tags.size()) {
+      const ProfTag& tg = g_prof_tags[i / 2];
+      Agg& a = agg[std::make_tuple(tg.N, tg.K, tg.epi, tg.M)];
+      a.n++; a.ms += t; a.flops += tg.flops;
+    }
+  }
+  g_prof_table.clear();
+  for (auto& kv : agg) {  // "M,N,K,epi,launches,ms,TFLOP/s;"
+    char buf[160];
+    snprintf(buf, sizeof(buf), "%d,%d,%d,%d,%lld,%.4f,%.1f;", std::get<3>(kv.first), std::get<0>(kv.first),
+             std::get<1>(kv.first), std::get<2>(kv.first), kv.second.n, kv.second.ms,
+             kv.second.ms > 0 ? kv.second.flops / kv.second.ms / 1e9 : 0.0);
+    g_prof_table += buf;
   }
   if (gemm_ms) *gemm_ms = ms;
   if (gemm_flops) *gemm_flops = g_prof_flops;

@@ -45,7 +45,7 @@ class KEEPModel(PreTrainedModel):
     base_model_prefix = ""
     _no_split_modules: list = []
     # image tiles per pass through the tower; bounds the activation workspace (~4.4 MB per tile)
-    image_chunk = 512
+    image_chunk = int(__import__("os").environ.get("KEEPB200_IMAGE_CHUNK", "512"))
     text_chunk_tokens = 1 << 18
 
     def __init__(self, config: KEEPConfig):
