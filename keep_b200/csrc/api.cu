@@ -215,7 +215,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- workspace layouts -------------------------------------------------------------------------------------
 struct ImageWs {
-  size_t x, xn, qkv, att, hid, cls16, h1, feat, total;
+  size_t x, xn, qkv, att, hid, xc, cls16, h1, feat, total;
 };
 ImageWs image_ws(const Model* m, int64_t n) {
   const KeepB200Config& c = m->cfg;
@@ -232,6 +232,7 @@ ImageWs image_ws(const Model* m, int64_t n) {
   size_t hid_bytes = M * F * 2;
   if (patch_bytes > hid_bytes) hid_bytes = patch_bytes;  // the patch matrix aliases the MLP hidden buffer
   w.hid = take(hid_bytes);
+  w.xc = take((size_t)n * D * 4);  // CLS rows of the residual stream (last block onwards)
   w.cls16 = take((size_t)n * D * 2);
   w.h1 = take((size_t)n * c.proj_dim * 2);
   w.feat = take((size_t)n * c.proj_dim * 4);
@@ -239,7 +240,7 @@ ImageWs image_ws(const Model* m, int64_t n) {
   return w;
 }
 struct TextWs {
-  size_t x32, x16, qkv, att, hid, pooled, total;
+  size_t x32, x16, qkv, att, hid, xc32, xc16, pooled, total;
 };
 TextWs text_ws(const Model* m, int64_t n, int64_t s) {
   const KeepB200Config& c = m->cfg;
@@ -252,6 +253,8 @@ TextWs text_ws(const Model* m, int64_t n, int64_t s) {
   w.qkv = take(M * 3 * d * 2);
   w.att = take(M * d * 2);
   w.hid = take(M * I * 2);
+  w.xc32 = take((size_t)n * d * 4);  // [CLS] rows (last layer onwards)
+  w.xc16 = take((size_t)n * d * 2);
   w.pooled = take((size_t)n * d * 4);
   w.total = off;
   return w;
@@ -259,10 +262,10 @@ TextWs text_ws(const Model* m, int64_t n, int64_t s) {
 
 int gemm(const void* A, int64_t lda, const void* W, int M, int N, int K, int epi, int bf16, const float* bias,
          const float* gamma, const float* resid, void* out, int64_t ldo, cudaStream_t st, const float* pos = nullptr,
-         int patches = 0) {
+         int patches = 0, int64_t ldr = -1) {
   GemmArgs a;
   a.A = A; a.lda = lda; a.W = W; a.ldw = K; a.M = M; a.N = N; a.K = K; a.epi = epi; a.bf16 = bf16;
-  a.bias = bias; a.gamma = gamma; a.resid = resid; a.ldr = ldo; a.out = out; a.ldo = ldo; a.pos = pos;
+  a.bias = bias; a.gamma = gamma; a.resid = resid; a.ldr = ldr < 0 ? ldo : ldr; a.out = out; a.ldo = ldo; a.pos = pos;
   a.patches = patches;
   return launch_gemm(a, st);
 }
@@ -277,6 +280,7 @@ int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, float
   void* qkv = ws + w.qkv;
   void* att = ws + w.att;
   void* hid = ws + w.hid;
+  float* xc = reinterpret_cast<float*>(ws + w.xc);
   void* cls16 = ws + w.cls16;
   void* h1 = ws + w.h1;
   float* feat = reinterpret_cast<float*>(ws + w.feat);
@@ -293,13 +297,23 @@ int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, float
     KB_TRY(launch_layernorm(x, D, M, D, b.n1w, b.n1b, c.vit_ln_eps, xn, bf, nullptr, st));
     KB_TRY(gemm(xn, D, b.qkv_w, M, 3 * D, D, EPI_BIAS_HALF, bf, b.qkv_b, nullptr, nullptr, qkv, 3 * D, st));
     KB_TRY(launch_attention(qkv, att, (int)n, T, c.vit_heads, bf, nullptr, 0, 0.125f, st));
-    KB_TRY(gemm(att, D, b.proj_w, M, D, D, EPI_RESID_F32, bf, b.proj_b, b.ls1, x, x, D, st));
-    KB_TRY(launch_layernorm(x, D, M, D, b.n2w, b.n2b, c.vit_ln_eps, xn, bf, nullptr, st));
-    KB_TRY(gemm(xn, D, b.fc1_w, M, F, D, EPI_BIAS_GELU_HALF, bf, b.fc1_b, nullptr, nullptr, hid, F, st));
-    KB_TRY(gemm(hid, F, b.fc2_w, M, D, F, EPI_RESID_F32, bf, b.fc2_b, b.ls2, x, x, D, st));
+    if (i + 1 < c.vit_depth) {
+      KB_TRY(gemm(att, D, b.proj_w, M, D, D, EPI_RESID_F32, bf, b.proj_b, b.ls1, x, x, D, st));
+      KB_TRY(launch_layernorm(x, D, M, D, b.n2w, b.n2b, c.vit_ln_eps, xn, bf, nullptr, st));
+      KB_TRY(gemm(xn, D, b.fc1_w, M, F, D, EPI_BIAS_GELU_HALF, bf, b.fc1_b, nullptr, nullptr, hid, F, st));
+      KB_TRY(gemm(hid, F, b.fc2_w, M, D, F, EPI_RESID_F32, bf, b.fc2_b, b.ls2, x, x, D, st));
+    } else {
+      // last block: only the CLS token is consumed downstream (global_pool='token'), and everything after the
+      // attention is row-wise, so proj / norm2 / fc1 / fc2 run on the n CLS rows (row pitch T*D) only
+      const int64_t pitch = (int64_t)T * D;
+      KB_TRY(gemm(att, pitch, b.proj_w, (int)n, D, D, EPI_RESID_F32, bf, b.proj_b, b.ls1, x, xc, D, st, nullptr, 0, pitch));
+      KB_TRY(launch_layernorm(xc, D, n, D, b.n2w, b.n2b, c.vit_ln_eps, cls16, bf, nullptr, st));
+      KB_TRY(gemm(cls16, D, b.fc1_w, (int)n, F, D, EPI_BIAS_GELU_HALF, bf, b.fc1_b, nullptr, nullptr, hid, F, st));
+      KB_TRY(gemm(hid, F, b.fc2_w, (int)n, D, F, EPI_RESID_F32, bf, b.fc2_b, b.ls2, xc, xc, D, st));
+    }
   }
-  // final norm on the CLS rows only (global_pool='token'), visual_head, L2-normalise
-  KB_TRY(launch_layernorm(x, (int64_t)T * D, n, D, m->norm_w, m->norm_b, c.vit_ln_eps, cls16, bf, nullptr, st));
+  // final norm on the CLS rows (global_pool='token'), visual_head, L2-normalise
+  KB_TRY(launch_layernorm(xc, D, n, D, m->norm_w, m->norm_b, c.vit_ln_eps, cls16, bf, nullptr, st));
   KB_TRY(gemm(cls16, D, m->h0_w, (int)n, c.proj_dim, D, EPI_BIAS_GELU_HALF, bf, m->h0_b, nullptr, nullptr, h1, c.proj_dim,
               st));
   KB_TRY(gemm(h1, c.proj_dim, m->h2_w, (int)n, c.proj_dim, c.proj_dim, EPI_BIAS_F32, bf, m->h2_b, nullptr, nullptr, feat,
@@ -319,6 +333,8 @@ int encode_text_chunk(Model* m, const int64_t* ids, const int64_t* tts, const in
   void* qkv = ws + w.qkv;
   void* att = ws + w.att;
   void* hid = ws + w.hid;
+  float* xc32 = reinterpret_cast<float*>(ws + w.xc32);
+  void* xc16 = ws + w.xc16;
   float* pooled = reinterpret_cast<float*>(ws + w.pooled);
   KB_TRY(launch_bert_embed(ids, tts, S, n, (int)se, d, m->word, m->ttype, m->tpos, m->emb_lnw, m->emb_lnb,
                            c.bert_ln_eps, x32, x16, bf, c.vocab_size, c.type_vocab, st));
@@ -327,14 +343,24 @@ int encode_text_chunk(Model* m, const int64_t* ids, const int64_t* tts, const in
     KB_TRY(gemm(x16, d, L.qkv_w, M, 3 * d, d, EPI_BIAS_HALF, bf, L.qkv_b, nullptr, nullptr, qkv, 3 * d, st));
     KB_TRY(launch_attention(qkv, att, (int)n, (int)se, c.heads, bf, mask, S, 0.125f, st));
     // post-LN: x = LN(x + dense(ctx)) ; x = LN(x + dense(gelu(dense(x))))
-    KB_TRY(gemm(att, d, L.ao_w, M, d, d, EPI_RESID_F32, bf, L.ao_b, nullptr, x32, x32, d, st));
-    KB_TRY(launch_layernorm(x32, d, M, d, L.ao_lnw, L.ao_lnb, c.bert_ln_eps, x16, bf, x32, st));
-    KB_TRY(gemm(x16, d, L.in_w, M, I, d, EPI_BIAS_GELU_HALF, bf, L.in_b, nullptr, nullptr, hid, I, st));
-    KB_TRY(gemm(hid, I, L.out_w, M, d, I, EPI_RESID_F32, bf, L.out_b, nullptr, x32, x32, d, st));
-    KB_TRY(launch_layernorm(x32, d, M, d, L.out_lnw, L.out_lnb, c.bert_ln_eps, x16, bf, x32, st));
+    if (i + 1 < c.layers) {
+      KB_TRY(gemm(att, d, L.ao_w, M, d, d, EPI_RESID_F32, bf, L.ao_b, nullptr, x32, x32, d, st));
+      KB_TRY(launch_layernorm(x32, d, M, d, L.ao_lnw, L.ao_lnb, c.bert_ln_eps, x16, bf, x32, st));
+      KB_TRY(gemm(x16, d, L.in_w, M, I, d, EPI_BIAS_GELU_HALF, bf, L.in_b, nullptr, nullptr, hid, I, st));
+      KB_TRY(gemm(hid, I, L.out_w, M, d, I, EPI_RESID_F32, bf, L.out_b, nullptr, x32, x32, d, st));
+      KB_TRY(launch_layernorm(x32, d, M, d, L.out_lnw, L.out_lnb, c.bert_ln_eps, x16, bf, x32, st));
+    } else {
+      // last layer: the pooler reads only the [CLS] row and everything after the attention is row-wise
+      const int64_t pitch = (int64_t)se * d;
+      KB_TRY(gemm(att, pitch, L.ao_w, (int)n, d, d, EPI_RESID_F32, bf, L.ao_b, nullptr, x32, xc32, d, st, nullptr, 0, pitch));
+      KB_TRY(launch_layernorm(xc32, d, n, d, L.ao_lnw, L.ao_lnb, c.bert_ln_eps, xc16, bf, xc32, st));
+      KB_TRY(gemm(xc16, d, L.in_w, (int)n, I, d, EPI_BIAS_GELU_HALF, bf, L.in_b, nullptr, nullptr, hid, I, st));
+      KB_TRY(gemm(hid, I, L.out_w, (int)n, d, I, EPI_RESID_F32, bf, L.out_b, nullptr, xc32, xc32, d, st));
+      KB_TRY(launch_layernorm(xc32, d, n, d, L.out_lnw, L.out_lnb, c.bert_ln_eps, xc16, bf, xc32, st));
+    }
   }
-  // pooler on the [CLS] rows (row pitch se*d), tanh, L2-normalise
-  KB_TRY(gemm(x16, (int64_t)se * d, m->pool_w, (int)n, d, d, EPI_BIAS_F32, bf, m->pool_b, nullptr, nullptr, pooled, d, st));
+  // pooler on the [CLS] rows, tanh, L2-normalise
+  KB_TRY(gemm(xc16, d, m->pool_w, (int)n, d, d, EPI_BIAS_F32, bf, m->pool_b, nullptr, nullptr, pooled, d, st));
   KB_TRY(launch_act_l2norm(pooled, n, d, 1, out, st));
   return KB_OK;
 }

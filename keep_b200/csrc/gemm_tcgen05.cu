@@ -182,6 +182,21 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
   }
 }
 
+// Residual epilogues stream 4 B/element from HBM; the read of tile i+1's residual block is started (into L2) while
+// tile i is being drained, so that the epilogue's loads hit L2 instead of paying the DRAM latency per 32x32 block.
+template <int EPI>
+__device__ __forceinline__ void prefetch_residual(const KParams& p, int lane, int row0, int col0, int ncols) {
+  if constexpr (EPI == EPI_RESID_F32) {
+    // this warp's block: 32 rows x ncols fp32 = ncols/32 lines of 128 B per row
+    const int lines_per_row = ncols >> 5;
+    for (int i = lane; i < 32 * lines_per_row; i += 32) {
+      const int r = row0 + i / lines_per_row, c = col0 + (i % lines_per_row) * 32;
+      if (r < p.M && c < p.N)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + (long long)r * p.ldr + c));
+    }
+  }
+}
+
 // ============================================================================================================
 // single-CTA tiles
 // ============================================================================================================
@@ -297,6 +312,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
+      {
+        const int nt = tile + gridDim.x;  // residual block of this warp in the CTA's next tile
+        if (nt < num_tiles)
+          prefetch_residual<EPI>(p, lane, (nt / n_tiles) * BLOCK_M + q * 32, (nt % n_tiles) * BN + half * (BN / 2), BN / 2);
+      }
       mbar_wait(&tfull_bar[as], aph, 4);
       tc_fence_after();
       epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * BLOCK_M + q * 32, n_blk * BN, half * (BN / 2),
@@ -437,6 +457,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
+      {
+        const int nt = tile + num_pairs;
+        if (nt < num_tiles)
+          prefetch_residual<EPI>(p, lane, (nt / n_tiles) * 2 * BLOCK_M + rank * BLOCK_M + q * 32,
+                                 (nt % n_tiles) * BN + half * (BN / 2), BN / 2);
+      }
       mbar_wait(&tfull_bar[as], aph, 14);
       tc_fence_after();
       epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * 2 * BLOCK_M + rank * BLOCK_M + q * 32, n_blk * BN,
