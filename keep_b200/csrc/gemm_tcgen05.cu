@@ -94,7 +94,10 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
   const uint32_t t_lane = tmem_acc + (uint32_t(q * 32) << 16);
 
   // one 32x32 block: accumulators of this lane's row in v[], `res` = prefetched residual (EPI_RESID_F32 only)
-  auto process = [&](const uint32_t (&v)[32], const float4 (&res)[8], int col) {
+  auto load_vec = [&](const float* base, int col, float fill) {
+    return base != nullptr ? __ldg(reinterpret_cast<const float4*>(base + col + tc)) : make_float4(fill, fill, fill, fill);
+  };
+  auto process = [&](const uint32_t (&v)[32], const float4 (&res)[8], int col, float4 b4, float4 g4) {
     // own row `lane` -> staging, 16-byte chunk j at (j ^ (lane & 7)): conflict-free for both access patterns
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -104,11 +107,6 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
                    : "memory");
     }
     __syncwarp();
-    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + tc));
-    if constexpr (EPI == EPI_RESID_F32) {
-      if (p.gamma != nullptr) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + tc));
-    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int rl = 4 * i + tr;
@@ -156,27 +154,39 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
         res[i] = (r < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)r * p.ldr + col + tc)
                            : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      const float4 b4 = load_vec(p.bias, col, 0.f), g4 = load_vec(p.gamma, col, 1.f);
       uint32_t v[32];
       tmem_ld_32x32(t_lane + uint32_t(c0), v);
       tmem_ld_wait();
-      process(v, res, col);
+      process(v, res, col, b4, g4);
     }
   } else {
     // software-pipelined: the TMEM load of the next block is in flight while this one is transformed and stored
     const float4 none[8] = {};
+    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
     uint32_t va[32], vb[32];
     int c_stop = c_end;
     if (n0 + c_stop > p.N) c_stop = p.N - n0;  // N is a multiple of 32
-    if (c_begin < c_stop) tmem_ld_32x32(t_lane + uint32_t(c_begin), va);
+    float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;  // bias of the block in flight, fetched with it
+    if (c_begin < c_stop) {
+      tmem_ld_32x32(t_lane + uint32_t(c_begin), va);
+      ba = load_vec(p.bias, n0 + c_begin, 0.f);
+    }
 #pragma unroll 1
     for (int c0 = c_begin; c0 < c_stop; c0 += 64) {
       tmem_ld_wait_dep(va);
-      if (c0 + 32 < c_stop) tmem_ld_32x32(t_lane + uint32_t(c0 + 32), vb);
-      process(va, none, n0 + c0);
+      if (c0 + 32 < c_stop) {
+        tmem_ld_32x32(t_lane + uint32_t(c0 + 32), vb);
+        bb = load_vec(p.bias, n0 + c0 + 32, 0.f);
+      }
+      process(va, none, n0 + c0, ba, one);
       if (c0 + 32 < c_stop) {
         tmem_ld_wait_dep(vb);
-        if (c0 + 64 < c_stop) tmem_ld_32x32(t_lane + uint32_t(c0 + 64), va);
-        process(vb, none, n0 + c0 + 32);
+        if (c0 + 64 < c_stop) {
+          tmem_ld_32x32(t_lane + uint32_t(c0 + 64), va);
+          ba = load_vec(p.bias, n0 + c0 + 64, 0.f);
+        }
+        process(vb, none, n0 + c0 + 32, bb, one);
       }
     }
   }
@@ -469,7 +479,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                          half * (BN / 2), (half + 1) * (BN / 2), stage);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[as]), 0));
     }
   }
 

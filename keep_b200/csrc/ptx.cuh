@@ -298,8 +298,14 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
   return r;
 }
-// arrive on an mbarrier that lives in another CTA of the cluster
+// arrive on an mbarrier that lives in another CTA of the cluster (release: orders this thread's prior memory
+// operations, at the price of a cluster-scope fence that also drains its outstanding global stores)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// relaxed variant for barriers that only hand back TMEM (ordered by tcgen05.fence::before_thread_sync, no
+// generic-proxy data is published): avoids stalling the epilogue warp on its in-flight global stores
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 }  // namespace kb
