@@ -138,7 +138,7 @@ def run_reference_arm(args, rank):
                          "sample": f"{sample} tiles per step (encode_image + 32-prompt similarity), fp32, {cpu}"},
         "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -150,7 +150,30 @@ def workload_name():
 # -------------------------------------------------------------------------------------------------------------
 # GPU arm
 # -------------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route fd 1 to stderr for the duration of the run (NCCL/driver chatter must not pollute the result line);
+    the single JSON line is written to the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -327,7 +350,7 @@ def main():
         }
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

@@ -162,6 +162,9 @@ int keepb200_op_layernorm(const float* x, int64_t row_stride, int64_t rows, int 
                           float eps, void* y16, int bf16, float* y32, void* stream);
 int keepb200_op_attention(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
                           int64_t mask_stride, float scale, void* stream);
+/* Debug/profiling aid: when dev_buf (device int64 [64*16]) is non-NULL the tcgen05 attention kernel's CTA 0 records
+ * clock64() stamps of its pipeline events for its first 64 work units; NULL switches tracing off. */
+int keepb200_debug_attention_trace(int64_t* dev_buf);
 int keepb200_op_act_l2norm(const float* x, int64_t rows, int D, int act, float* y, void* stream);
 
 #ifdef __cplusplus

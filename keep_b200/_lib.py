@@ -70,6 +70,7 @@ SIGNATURES = {
     "keepb200_op_gemm": (_int, [_p, _i64, _p, _i64, _int, _int, _int, _int, _int, _p, _p, _p, _i64, _p, _i64, _p, _int, _p]),
     "keepb200_op_layernorm": (_int, [_p, _i64, _i64, _int, _p, _p, _f, _p, _int, _p, _p]),
     "keepb200_op_attention": (_int, [_p, _p, _int, _int, _int, _int, _p, _i64, _f, _p]),
+    "keepb200_debug_attention_trace": (_int, [_p]),
     "keepb200_op_act_l2norm": (_int, [_p, _i64, _int, _int, _p, _p]),
 }
 

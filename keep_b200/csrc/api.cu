@@ -605,6 +605,10 @@ int keepb200_op_attention(const void* qkv, void* out, int B, int S, int H, int b
                           int64_t mask_stride, float scale, void* stream) {
   return launch_attention(qkv, out, B, S, H, bf16, key_mask, mask_stride, scale, static_cast<cudaStream_t>(stream));
 }
+int keepb200_debug_attention_trace(int64_t* dev_buf) {
+  attention_tc_set_trace(reinterpret_cast<long long*>(dev_buf));
+  return KB_OK;
+}
 int keepb200_op_act_l2norm(const float* x, int64_t rows, int D, int act, float* y, void* stream) {
   return launch_act_l2norm(x, rows, D, act, y, static_cast<cudaStream_t>(stream));
 }

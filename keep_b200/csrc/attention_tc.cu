@@ -42,6 +42,7 @@ struct AtcParams {
   uint32_t idesc_s;   // 128 x S_pad, both operands K-major
   uint32_t idesc_pv;  // 128 x 64, B (V) MN-major
   int bf16;
+  long long* trace;   // optional [64 units][16 events] clock64 stamps of CTA 0 (debug/profiling aid), or null
 };
 
 struct Smem {  // offsets inside the 1024-aligned dynamic smem block
@@ -67,6 +68,15 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int bf16) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+
+// event slots of the optional trace (per unit)
+enum { EV_S_ISSUE = 0, EV_PV_WAITED = 1, EV_PV_ISSUED = 2, EV_SM_START = 3, EV_SM_P1 = 4, EV_SM_BATON = 5, EV_SM_P2 = 6,
+       EV_OUT_START = 7, EV_OUT_DONE = 8 };
+#define ATC_TRACE(u, ev)                                                                         \
+  do {                                                                                           \
+    if (p.trace != nullptr && blockIdx.x == 0 && (u) < 64 && (threadIdx.x & 127) == 0)           \
+      p.trace[(u) * 16 + (ev)] = clock64();                                                      \
+  } while (0)
 
 __global__ void __launch_bounds__(kAtcThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
@@ -172,6 +182,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         for (int k = 0; k < 4; ++k)  // head dim 64 = 4 x 16
           umma_f16_ss(tmem_base + r * p.S_pad, dq + 2 * k, dk + 2 * k, p.idesc_s, k != 0 ? 1u : 0u);
         umma_commit(&s_ready[r]);
+        if (p.trace != nullptr && blockIdx.x == 0 && u < 64) p.trace[u * 16 + EV_S_ISSUE] = clock64();
         if (t == p.n_qt - 1) umma_commit(&qk_empty[qs]);  // Q/K of this head are dead once these MMAs complete
       };
       auto issue_pv = [&](int u) {
@@ -180,11 +191,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         if (t == 0) mbar_wait(&v_full[vs], (j / 3) & 1, 25);
         if (u > 0) mbar_wait(o_free, (u - 1) & 1, 26);  // the output group has drained O of the previous unit
         tc_fence_after();
+        if (p.trace != nullptr && blockIdx.x == 0 && u < 64) p.trace[u * 16 + EV_PV_WAITED] = clock64();
         const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + Smem::v + vs * V_SLOT_BYTES));
         const int ksteps = p.S_pad / 16;
         for (int k = 0; k < ksteps; ++k)  // 16 keys per MMA: P advances 8 TMEM columns, V advances 16 rows = 2048 B
           umma_f16_ts(tmem_base + o_col, tmem_base + r * p.S_pad + 8 * k, dv + 128 * k, p.idesc_pv, k != 0 ? 1u : 0u);
         umma_commit(o_ready);
+        if (p.trace != nullptr && blockIdx.x == 0 && u < 64) p.trace[u * 16 + EV_PV_ISSUED] = clock64();
         if (t == p.n_qt - 1) umma_commit(&v_empty[vs]);
       };
       if (U > 0) issue_s(0);
@@ -212,88 +225,115 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const int slow_end = live ? p.S_pad : 0;
       mbar_wait(&s_ready[g], n & 1, 28);
       tc_fence_after();
-      // ---- pass 1: row max of scale*s + bias (scale > 0, so the raw max is taken where there is no bias) ----
-      float mx_raw = -INFINITY, mx = -INFINITY;
-      uint32_t va[32], vb[32];
-      if (fast_end > 0) tmem_ld_32x32(t_row, va);
-      for (int c = 0; c < fast_end; c += 64) {  // software-pipelined: the next chunk is in flight while this one is reduced
-        tmem_ld_wait_dep(va);
-        if (c + 32 < fast_end) tmem_ld_32x32(t_row + c + 32, vb);
+      ATC_TRACE(u, EV_SM_START);
+      // ---- single pass over S: TMEM read bandwidth (~64 B/clk/SM) is the scarce resource of this kernel, so S is
+      // read exactly once. p = exp2(scale*s + bias - m_ref) with a LAZY reference: m_ref starts as ceil(max of the
+      // first block) and is raised (to an integer, so the rescale factor is an exact power of two) only when a later
+      // block exceeds it by more than 2^10; the P blocks already written are then rescaled in place. softmax is
+      // shift-invariant, so O / sum is unchanged; P <= 2^10 stays far inside the fp16 range.
+      float m_ref = -INFINITY, sum = 0.f;
+      auto raise_ref = [&](float cm, int c_done) {  // warp-uniform call; cm = this lane's block max (log2 domain)
+        const bool need = cm > m_ref + 10.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_new = need ? ceilf(cm) : m_ref;
+          const float f = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);  // exact power of two, or 1
+          sum *= f;
+          uint32_t f2;
+          if (p.bf16) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f, f);
+            f2 = *reinterpret_cast<uint32_t*>(&h);
+          } else {
+            __half2 h = __floats2half2_rn(f, f);
+            f2 = *reinterpret_cast<uint32_t*>(&h);
+          }
+          if (c_done > 0) tmem_st_wait();  // the P blocks stored so far must have landed before they are re-read
+          for (int cc = 0; cc < c_done; cc += 16) {  // P blocks written so far: 16 keys = 8 packed columns each
+            uint32_t w[8];
+            tmem_ld_32x8(t_row + (cc >> 1), w);
+            tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, __uint_as_float(va[i]));
-        if (c + 32 < fast_end) {
-          tmem_ld_wait_dep(vb);
-          if (c + 64 < fast_end) tmem_ld_32x32(t_row + c + 64, va);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, __uint_as_float(vb[i]));
+            for (int i = 0; i < 8; ++i) {
+              if (p.bf16) {
+                __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&w[i]), *reinterpret_cast<__nv_bfloat162*>(&f2));
+                w[i] = *reinterpret_cast<uint32_t*>(&r);
+              } else {
+                __half2 r = __hmul2(*reinterpret_cast<__half2*>(&w[i]), *reinterpret_cast<__half2*>(&f2));
+                w[i] = *reinterpret_cast<uint32_t*>(&r);
+              }
+            }
+            tmem_st_32x8(t_row + (cc >> 1), w);
+          }
+          m_ref = m_new;
         }
-      }
-      for (int c = fast_end; c < slow_end; c += 16) {
-        uint32_t v[16];
-        tmem_ld_32x16(t_row + c, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias + c + i);
-          mx = fmaxf(mx, fmaf(__uint_as_float(v[i]), p.scale_log2, b4.x));
-          mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 1]), p.scale_log2, b4.y));
-          mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 2]), p.scale_log2, b4.z));
-          mx = fmaxf(mx, fmaf(__uint_as_float(v[i + 3]), p.scale_log2, b4.w));
-        }
-      }
-      mx = fmaxf(mx, mx_raw * p.scale_log2);
-      if (mx == -INFINITY) mx = 0.f;  // fully masked row: avoid (-inf) - (-inf)
-      const float neg_mx = -mx;
-      // ---- pass 2: p = exp2(scale*s + bias - max), row sum, P (16-bit) written over S ----
-      // baton: wait until the other group has finished its exp2 pass (group 0's first unit goes first)
-      if (g == 1) mbar_wait(&turn[1], n & 1, 29);
-      else if (n > 0) mbar_wait(&turn[0], (n - 1) & 1, 30);
-      float sum = 0.f;
+      };
       auto exp_chunk = [&](const uint32_t (&v)[32], int c) {
+        float c0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), c1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+        float c2 = fmaxf(__uint_as_float(v[4]), __uint_as_float(v[5])), c3 = fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7]));
+#pragma unroll
+        for (int i = 8; i < 32; i += 4) {  // four independent chains: short dependency depth
+          c0 = fmaxf(c0, __uint_as_float(v[i]));
+          c1 = fmaxf(c1, __uint_as_float(v[i + 1]));
+          c2 = fmaxf(c2, __uint_as_float(v[i + 2]));
+          c3 = fmaxf(c3, __uint_as_float(v[i + 3]));
+        }
+        raise_ref(fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)) * p.scale_log2, c);
+        const float neg_m = -m_ref;
+        float s0 = 0.f, s1 = 0.f;
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float e0 = ex2f(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_mx));
-          const float e1 = ex2f(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_mx));
-          sum += e0 + e1;
+          const float e0 = ex2f(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_m));
+          const float e1 = ex2f(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_m));
+          s0 += e0;
+          s1 += e1;
           pk[i] = pack16(e0, e1, p.bf16);
         }
+        sum += s0 + s1;
         tmem_st_32x16(t_row + (c >> 1), pk);
       };
+      ATC_TRACE(u, EV_SM_P1);
+      ATC_TRACE(u, EV_SM_BATON);
+      uint32_t va[32], vb[32];
       if (fast_end > 0) tmem_ld_32x32(t_row, va);
-      for (int c = 0; c < fast_end; c += 64) {
-        tmem_ld_wait_dep(va);
-        if (c + 32 < fast_end) tmem_ld_32x32(t_row + c + 32, vb);
+      if (fast_end > 32) tmem_ld_32x32(t_row + 32, vb);
+      for (int c = 0; c < fast_end; c += 64) {  // two loads in flight while a block is processed
+        tmem_ld_wait_dep(va);                    // (wait::ld covers both outstanding loads: vb is complete as well)
         exp_chunk(va, c);
+        if (c + 64 < fast_end) tmem_ld_32x32(t_row + c + 64, va);
         if (c + 32 < fast_end) {
           tmem_ld_wait_dep(vb);
-          if (c + 64 < fast_end) tmem_ld_32x32(t_row + c + 64, va);
           exp_chunk(vb, c + 32);
+          if (c + 96 < fast_end) tmem_ld_32x32(t_row + c + 96, vb);
         }
       }
-      for (int c = fast_end; c < slow_end; c += 16) {
+      for (int c = fast_end; c < slow_end; c += 16) {  // blocks that contain masked keys: additive 0 / -inf bias
         uint32_t v[16];
         tmem_ld_32x16(t_row + c, v);
         tmem_ld_wait();
+        float t[16];
+        float cm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + c + i);
+          t[i] = fmaf(__uint_as_float(v[i]), p.scale_log2, b4.x);
+          t[i + 1] = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, b4.y);
+          t[i + 2] = fmaf(__uint_as_float(v[i + 2]), p.scale_log2, b4.z);
+          t[i + 3] = fmaf(__uint_as_float(v[i + 3]), p.scale_log2, b4.w);
+          cm = fmaxf(fmaxf(cm, fmaxf(t[i], t[i + 1])), fmaxf(t[i + 2], t[i + 3]));
+        }
+        raise_ref(cm, c);
+        const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;  // everything masked so far: exp2(-inf) = 0
         uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias + c + 2 * i);
-          const float e0 = ex2f(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, b4.x + neg_mx));
-          const float e1 = ex2f(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, b4.y + neg_mx));
-          const float e2 = ex2f(fmaf(__uint_as_float(v[2 * i + 2]), p.scale_log2, b4.z + neg_mx));
-          const float e3 = ex2f(fmaf(__uint_as_float(v[2 * i + 3]), p.scale_log2, b4.w + neg_mx));
-          sum += (e0 + e1) + (e2 + e3);
+        for (int i = 0; i < 8; ++i) {
+          const float e0 = ex2f(t[2 * i] + neg_m), e1 = ex2f(t[2 * i + 1] + neg_m);
+          sum += e0 + e1;
           pk[i] = pack16(e0, e1, p.bf16);
-          pk[i + 1] = pack16(e2, e3, p.bf16);
         }
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(t_row + (c >> 1)),
-                     "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                     : "memory");
+        tmem_st_32x8(t_row + (c >> 1), pk);
       }
+      ATC_TRACE(u, EV_SM_P2);
       s_rowsum[(g * 2 + (n & 1)) * 128 + row_in_tile] = sum;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&turn[g ^ 1]);  // the other group may start its exp2 pass
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -312,6 +352,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const float sum = s_rowsum[(r * 2 + (n & 1)) * 128 + row_in_tile];
       mbar_wait(o_ready, u & 1, 32);
       tc_fence_after();
+      ATC_TRACE(u, EV_OUT_START);
       uint32_t va[32], vb[32];
       if (t * 128 + q * 32 < p.S) {  // warp-uniform: skip the tail warps of the last tile
         tmem_ld_32x32(t_o, va);
@@ -322,6 +363,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_free);  // O may be overwritten by the next PV
+      ATC_TRACE(u, EV_OUT_DONE);
       const float inv = sum > 0.f ? 1.0f / sum : 0.f;
       const int srow = t * 128 + row_in_tile;
       if (srow < p.S) {
@@ -358,6 +400,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
 }  // namespace
 
+static long long* g_atc_trace = nullptr;
+void attention_tc_set_trace(long long* dev_buf) { g_atc_trace = dev_buf; }
+
 bool attention_tc_supports(int S) { return S > 64 && (S + 15) / 16 * 16 <= kMaxSpad; }
 
 int launch_attention_tc(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
@@ -387,6 +432,7 @@ int launch_attention_tc(const void* qkv, void* out, int B, int S, int H, int bf1
   p.idesc_s = make_idesc(fmt, 128, S_pad, 0, 0);
   p.idesc_pv = make_idesc(fmt, 128, 64, 0, 1);  // B operand (V) is MN-major: rows are keys, 64 head-dim values contiguous
   p.bf16 = bf16;
+  p.trace = g_atc_trace;
   int grid = num_sms();
   if (p.items < grid) grid = p.items;
   attention_tc_kernel<<<grid, kAtcThreads, smem, stream>>>(tq, tkv, p);

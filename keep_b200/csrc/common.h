@@ -84,6 +84,7 @@ int launch_attention(const void* qkv, void* out, int B, int S, int H, int bf16, 
 
 // tcgen05 variant (64 < S <= 224); launch_attention dispatches to it unless KEEPB200_ATTN=v1
 bool attention_tc_supports(int S);
+void attention_tc_set_trace(long long* dev_buf);  // debug aid: clock64 stamps of CTA 0, [64 units][16 events]
 int launch_attention_tc(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
                         int64_t mask_stride, float scale, cudaStream_t stream);
 

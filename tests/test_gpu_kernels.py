@@ -168,6 +168,27 @@ def test_attention(B, S, H, masked, dtype):
     assert _rel(out, ref) < (2e-3 if dtype == torch.float16 else 1.5e-2)
 
 
+def test_attention_late_maximum_triggers_rescale():
+    """The tcgen05 kernel reads S once with a lazily raised softmax reference; rows whose maximum sits in a late
+    key block, ~2^30 above the first block, must come out identical to the two-pass result."""
+    from keep_b200 import ops
+
+    B, S, H = 2, 197, 16
+    g = torch.Generator().manual_seed(77)
+    qkv = (torch.randn(B * S, 3 * H * 64, generator=g) * 0.5).view(B, S, 3, H, 64)
+    # make key 150 (5th block) align strongly with every query of head 3, and key 196 (masked-path block) with head 5
+    qkv[:, :, 0, 3, :] = 3.0
+    qkv[:, 150, 1, 3, :] = 4.0
+    qkv[:, :, 0, 5, :] = -2.0
+    qkv[:, 196, 1, 5, :] = -5.0
+    qkv = qkv.reshape(B * S, 3 * H * 64).half().to(DEV)
+    out = ops.attention(qkv, B, S, H)
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = F.scaled_dot_product_attention(q, k, v, scale=0.125).transpose(1, 2).reshape(B * S, H * 64)
+    assert torch.isfinite(out).all()
+    assert _rel(out, ref) < 2e-3
+
+
 def test_similarity_and_group_softmax():
     from keep_b200 import ops
 
