@@ -124,14 +124,20 @@ int keepb200_encode_text(void* handle, const int64_t* ids, const int64_t* type_i
 /* logits[N,P] = normalize(feats)[N,D] @ cls[D,P];  probs[N,P] = softmax(temp * logits) over each
  * consecutive group of `group` columns (0 = one group of all P columns, the reference's single
  * classifier [D,C]; K stacked classifiers of C classes use group = C). feats and cls are fp32, cls in the
- * reference's [D,P] layout (utils.py:83). logits or probs may be NULL (not both). D % 4 == 0. */
+ * reference's [D,P] layout (utils.py:83). logits is required, probs may be NULL. D % 4 == 0.
+ * workspace: P*D*4 bytes (keepb200_similarity_workspace_bytes) for the K-major copy of the classifier used by
+ * the TF32 tcgen05 kernel (D % 32 == 0); with workspace == NULL the fp32 FMA kernel runs instead. */
 int keepb200_similarity(const float* feats, int64_t N, int64_t D, const float* cls, int64_t P, int group,
-                        float temp, float* logits, float* probs, void* stream);
+                        float temp, float* logits, float* probs, void* workspace, size_t workspace_bytes,
+                        void* stream);
+size_t keepb200_similarity_workspace_bytes(int64_t D, int64_t P);
 
 /* Prompt screening (utils.py:107-146): for K classifiers of C classes stacked as cls[D, K*C], with
  * logits_k = normalize(feats) @ cls_k: scores[k] = mean_n( top1 - top2 - |top1 + top2 - 1| ). */
 int keepb200_prompt_scores(const float* feats, int64_t N, int64_t D, const float* cls, int64_t K, int64_t C,
                            float* scores, void* workspace, size_t workspace_bytes, void* stream);
+/* minimum workspace: K*C*D*4 (K-major classifier copy) + 64 rows of logits; more rows = fewer passes */
+size_t keepb200_prompt_scores_workspace_bytes(int64_t N, int64_t D, int64_t K, int64_t C);
 
 /* refine_seg (detection_utils.py:39-74 et al.): coords int64 [N,2] (x,y), probs fp32 [N,C].
  * First occurrence of a coordinate wins; with overlap != 0 every kept tile's probabilities are replaced by

@@ -59,7 +59,9 @@ SIGNATURES = {
     "keepb200_workspace_bytes": (_sz, [_p, _int, _i64, _i64]),
     "keepb200_encode_image": (_int, [_p, _p, _int, _i64, _p, _p, _sz, _p]),
     "keepb200_encode_text": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _sz, _p]),
-    "keepb200_similarity": (_int, [_p, _i64, _i64, _p, _i64, _int, _f, _p, _p, _p]),
+    "keepb200_similarity": (_int, [_p, _i64, _i64, _p, _i64, _int, _f, _p, _p, _p, _sz, _p]),
+    "keepb200_similarity_workspace_bytes": (_sz, [_i64, _i64]),
+    "keepb200_prompt_scores_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "keepb200_prompt_scores": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _sz, _p]),
     "keepb200_refine": (_int, [_p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _sz, _p]),
     "keepb200_refine_workspace_bytes": (_sz, [_i64]),

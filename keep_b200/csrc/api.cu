@@ -536,12 +536,24 @@ int keepb200_encode_text(void* handle, const int64_t* ids, const int64_t* type_i
   return KB_OK;
 }
 
+size_t keepb200_similarity_workspace_bytes(int64_t D, int64_t P) { return (D > 0 && P > 0) ? (size_t)D * P * 4 : 0; }
+
 int keepb200_similarity(const float* feats, int64_t N, int64_t D, const float* cls, int64_t P, int group, float temp,
-                        float* logits, float* probs, void* stream) {
+                        float* logits, float* probs, void* workspace, size_t workspace_bytes, void* stream) {
   if (N == 0 || P == 0) return KB_OK;
   if (!feats || !cls || N < 0 || P < 0 || D <= 0) return set_error(KB_ERR_ARG, "similarity: bad arguments");
   if (P > (1 << 30)) return set_error(KB_ERR_ARG, "similarity: P too large");
-  return launch_similarity(feats, N, (int)D, cls, (int)P, group, temp, logits, probs, static_cast<cudaStream_t>(stream));
+  float* clsT = nullptr;
+  if (workspace != nullptr && workspace_bytes >= (size_t)D * P * 4 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0)
+    clsT = static_cast<float*>(workspace);
+  return launch_similarity(feats, N, (int)D, cls, (int)P, group, temp, logits, probs, static_cast<cudaStream_t>(stream), clsT);
+}
+
+size_t keepb200_prompt_scores_workspace_bytes(int64_t N, int64_t D, int64_t K, int64_t C) {
+  if (N <= 0 || D <= 0 || K <= 0 || C <= 0) return 0;
+  const size_t P = (size_t)K * C;
+  const size_t rows = (size_t)((N + 63) / 64 * 64);
+  return P * D * 4 + rows * P * 4;
 }
 
 int keepb200_prompt_scores(const float* feats, int64_t N, int64_t D, const float* cls, int64_t K, int64_t C,
@@ -550,17 +562,22 @@ int keepb200_prompt_scores(const float* feats, int64_t N, int64_t D, const float
   if (!feats || !cls || !scores || N <= 0 || K < 0 || C < 2 || D <= 0) return set_error(KB_ERR_ARG, "prompt_scores: bad arguments");
   const int64_t P = K * C;
   const size_t row_bytes = (size_t)P * 4;
-  if (!workspace || workspace_bytes < row_bytes * 64)
-    return set_error(KB_ERR_WORKSPACE, "prompt_scores: workspace %zu B < %zu B (64 rows of logits)", workspace_bytes, row_bytes * 64);
+  const size_t clsT_bytes = (size_t)P * D * 4;
+  if (!workspace || workspace_bytes < clsT_bytes + row_bytes * 64)
+    return set_error(KB_ERR_WORKSPACE, "prompt_scores: workspace %zu B < %zu B (classifier copy + 64 rows of logits)",
+                     workspace_bytes, clsT_bytes + row_bytes * 64);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   KB_CUDA_CHECK(cudaMemsetAsync(scores, 0, (size_t)K * 4, st));
-  int64_t chunk = (int64_t)(workspace_bytes / row_bytes);
+  float* clsT = static_cast<float*>(workspace);
+  float* logits = reinterpret_cast<float*>(static_cast<char*>(workspace) + ((clsT_bytes + 1023) / 1024 * 1024));
+  const size_t avail = workspace_bytes - ((clsT_bytes + 1023) / 1024 * 1024);
+  int64_t chunk = (int64_t)(avail / row_bytes);
   chunk = chunk / 64 * 64;
+  if (chunk < 64) return set_error(KB_ERR_WORKSPACE, "prompt_scores: workspace too small for 64 rows of logits");
   if (chunk > N) chunk = N;
-  float* logits = static_cast<float*>(workspace);
   for (int64_t r0 = 0; r0 < N; r0 += chunk) {
     const int64_t n = (N - r0 < chunk) ? (N - r0) : chunk;
-    KB_TRY(launch_similarity(feats + r0 * D, n, (int)D, cls, (int)P, (int)C, 1.0f, logits, nullptr, st));
+    KB_TRY(launch_similarity(feats + r0 * D, n, (int)D, cls, (int)P, (int)C, 1.0f, logits, nullptr, st, clsT));
     KB_TRY(launch_prompt_score_accum(logits, n, (int)K, (int)C, scores, st));
   }
   return launch_scale(scores, K, 1.0f / (float)N, st);

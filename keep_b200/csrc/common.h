@@ -106,8 +106,11 @@ int launch_bert_embed(const int64_t* ids, const int64_t* tts, int64_t id_stride,
 // ---- similarity -------------------------------------------------------------------------------------------------
 // logits[n,p] = <feats[n,:]/max(||feats[n]||,1e-12), cls[:,p]> ; probs = softmax over each consecutive
 // group of `group` columns of (temp * logits). feats fp32 [N,D], cls fp32 [D,P] (torch layout, utils.py:83).
+// clsT_scratch: optional device buffer of P*D floats; when given (and D % 32 == 0) the TF32 tcgen05 kernel is used.
 int launch_similarity(const float* feats, int64_t N, int D, const float* cls, int P, int group, float temp,
-                      float* logits, float* probs, cudaStream_t stream);
+                      float* logits, float* probs, cudaStream_t stream, float* clsT_scratch = nullptr);
+int launch_similarity_tc(const float* feats, int64_t N, int D, const float* clsT, int P, int group, float temp,
+                         float* logits, float* probs, bool* fused_probs, cudaStream_t stream);
 // scores[k] += sum_n(top1 - top2 - |top1 + top2 - 1|) over logits[n, k*C:(k+1)*C]  (scale by 1/N afterwards)
 int launch_prompt_score_accum(const float* logits, int64_t rows, int K, int C, float* scores, cudaStream_t stream);
 int launch_scale(float* v, int64_t n, float s, cudaStream_t stream);

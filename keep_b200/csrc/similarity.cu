@@ -10,6 +10,9 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace kb {
 namespace {
 
@@ -130,12 +133,32 @@ __global__ void scale_kernel(float* v, long long n, float s) {
 }  // namespace
 
 int launch_similarity(const float* feats, int64_t N, int D, const float* cls, int P, int group, float temp,
-                      float* logits, float* probs, cudaStream_t stream) {
+                      float* logits, float* probs, cudaStream_t stream, float* clsT_scratch) {
   if (N <= 0 || P <= 0) return KB_OK;
   if (D % 4 != 0) return set_error(KB_ERR_ARG, "similarity: D=%d must be a multiple of 4", D);
   if (logits == nullptr) return set_error(KB_ERR_ARG, "similarity: logits buffer is required");
   if (group <= 0) group = P;
   if (P % group != 0) return set_error(KB_ERR_ARG, "similarity: P=%d is not a multiple of group=%d", P, group);
+  static int force_fma = -1;
+  if (force_fma < 0) {
+    const char* e = std::getenv("KEEPB200_SIM");
+    force_fma = (e && !std::strcmp(e, "fma")) ? 1 : 0;
+  }
+  if (clsT_scratch != nullptr && D % 32 == 0 && !force_fma && (reinterpret_cast<uintptr_t>(feats) & 15) == 0) {
+    // tensor-core path: classifier transposed to K-major [P, D] (tiny), TF32 tcgen05 GEMM with fused epilogue
+    int rc = launch_transpose_f32(cls, clsT_scratch, D, P, stream);
+    if (rc) return rc;
+    bool fused = false;
+    rc = launch_similarity_tc(feats, N, D, clsT_scratch, P, group, temp, logits, probs, &fused, stream);
+    if (rc) return rc;
+    if (probs != nullptr && !fused) {
+      const long long n = N * (P / group);
+      group_softmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(logits, N, P, group, temp, probs);
+      note_launch();
+      KB_CUDA_CHECK(cudaGetLastError());
+    }
+    return KB_OK;
+  }
   dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)((P + BN - 1) / BN));
   sim_gemm_kernel<<<grid, 256, 0, stream>>>(feats, N, D, cls, P, logits);
   note_launch();

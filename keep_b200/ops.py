@@ -94,8 +94,9 @@ def act_l2norm(x, act=0):
     return y
 
 
-def similarity(feats, cls, group=0, temp=10.0, want_probs=True):
-    """logits = normalize(feats) @ cls ; probs = softmax(temp*logits) per `group` columns (0 = all)."""
+def similarity(feats, cls, group=0, temp=10.0, want_probs=True, tensor_cores=True):
+    """logits = normalize(feats) @ cls ; probs = softmax(temp*logits) per `group` columns (0 = all).
+    tensor_cores=True: TF32 tcgen05 kernel (needs D % 32 == 0); False: fp32 FMA kernel (bit-closer to fp32)."""
     _need_cuda(feats, cls)
     feats = feats.contiguous().float()
     cls = cls.contiguous().float()
@@ -105,9 +106,11 @@ def similarity(feats, cls, group=0, temp=10.0, want_probs=True):
     logits = torch.empty(N, P, dtype=torch.float32, device=feats.device)
     probs = torch.empty(N, P, dtype=torch.float32, device=feats.device) if want_probs else None
     L = _lib.lib()
+    ws_bytes = L.keepb200_similarity_workspace_bytes(D, P) if tensor_cores else 0
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=feats.device) if tensor_cores else None
     _lib.check(
         L.keepb200_similarity(feats.data_ptr(), N, D, cls.data_ptr(), P, group, temp, logits.data_ptr(), _lib.ptr(probs),
-                              _lib.stream_ptr(feats.device)),
+                              _lib.ptr(ws), ws_bytes, _lib.stream_ptr(feats.device)),
         "similarity",
     )
     return logits, probs
@@ -121,9 +124,11 @@ def prompt_scores(feats, cls, K, C, workspace_mb=256):
     N, D = feats.shape
     assert cls.shape == (D, K * C)
     scores = torch.empty(K, dtype=torch.float32, device=feats.device)
-    ws_bytes = max(64 * K * C * 4, min(workspace_mb << 20, ((N + 63) // 64) * 64 * K * C * 4))
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device)
     L = _lib.lib()
+    full = L.keepb200_prompt_scores_workspace_bytes(N, D, K, C)
+    minimum = L.keepb200_prompt_scores_workspace_bytes(64, D, K, C)
+    ws_bytes = max(minimum, min(full, (workspace_mb << 20) + minimum))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device)
     _lib.check(
         L.keepb200_prompt_scores(feats.data_ptr(), N, D, cls.data_ptr(), K, C, scores.data_ptr(), ws.data_ptr(), ws_bytes,
                                  _lib.stream_ptr(feats.device)),

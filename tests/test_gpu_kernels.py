@@ -189,22 +189,33 @@ def test_attention_late_maximum_triggers_rescale():
     assert _rel(out, ref) < 2e-3
 
 
-def test_similarity_and_group_softmax():
+@pytest.mark.parametrize("tensor_cores", [True, False])
+def test_similarity_and_group_softmax(tensor_cores):
+    """TF32 tcgen05 kernel (10-bit operand mantissa: cosine error ~3e-5, gate 1e-3) and the fp32 FMA kernel."""
     from keep_b200 import ops
 
+    tol_l, tol_p = (2e-4, 1e-3) if tensor_cores else (1e-5, 1e-5)
     feats = torch.randn(1000, 768, device=DEV) * 2
     cls = F.normalize(torch.randn(768, 32, device=DEV), dim=0)
-    logits, probs = ops.similarity(feats, cls, group=2, temp=10.0)
+    logits, probs = ops.similarity(feats, cls, group=2, temp=10.0, tensor_cores=tensor_cores)
     ref = F.normalize(feats, dim=-1) @ cls
-    assert _rel(logits, ref) < 1e-5
-    assert _rel(probs, torch.softmax(ref.view(1000, 16, 2) * 10, -1).view(1000, 32)) < 1e-5
-    for P in (2, 3, 4, 256, 70):  # ragged prompt counts
+    assert (logits - ref).abs().max().item() < tol_l
+    assert (probs - torch.softmax(ref.view(1000, 16, 2) * 10, -1).view(1000, 32)).abs().max().item() < tol_p
+    for P, group in ((2, 0), (3, 0), (4, 4), (256, 4), (70, 0), (640, 2), (48, 16), (96, 32)):  # ragged prompt counts / groupings
         c = F.normalize(torch.randn(768, P, device=DEV), dim=0)
-        lg, pr = ops.similarity(feats[:333], c)
+        lg, pr = ops.similarity(feats[:333], c, group=group, tensor_cores=tensor_cores)
         r = F.normalize(feats[:333], dim=-1) @ c
-        assert _rel(lg, r) < 1e-5 and _rel(pr, torch.softmax(r * 10, 1)) < 1e-5
-    lg, pr = ops.similarity(feats[:0], cls)
+        g = group or P
+        assert (lg - r).abs().max().item() < tol_l, (P, group)
+        assert (pr - torch.softmax(r.view(333, P // g, g) * 10, -1).view(333, P)).abs().max().item() < tol_p, (P, group)
+    lg, pr = ops.similarity(feats[:0], cls, tensor_cores=tensor_cores)
     assert lg.shape == (0, 32)
+    big = torch.randn(20000, 768, device=DEV)
+    lg, _ = ops.similarity(big, cls, group=2, tensor_cores=tensor_cores)  # many tiles per CTA: persistent loop, TMEM double buffer
+    assert (lg - F.normalize(big, dim=-1) @ cls).abs().max().item() < tol_l
+    zero = torch.zeros(5, 768, device=DEV)
+    lg, pr = ops.similarity(zero, cls[:, :2], tensor_cores=tensor_cores)   # eps clamp: 0 / max(0, 1e-12)
+    assert torch.equal(lg, torch.zeros(5, 2, device=DEV)) and (pr - 0.5).abs().max().item() < 1e-6
 
 
 def test_prompt_scores_chunked():
@@ -217,7 +228,7 @@ def test_prompt_scores_chunked():
     lg = (F.normalize(feats, dim=-1) @ cls).view(N, K, C)
     top = lg.topk(2, dim=2).values
     ref = ((top[..., 0] - top[..., 1]) - (top[..., 0] + top[..., 1] - 1).abs()).mean(0)
-    assert (s - ref).abs().max().item() < 1e-5
+    assert (s - ref).abs().max().item() < 1e-4
 
 
 @pytest.mark.parametrize("overlap", [True, False])

@@ -178,6 +178,26 @@ def bench_attention():
         print(f"[perf] attention B={B} S={S} H={H} mask={int(masked)}: {ms:.3f} ms = {fl / ms / 1e9:.0f} TFLOP/s", flush=True)
 
 
+def bench_similarity():
+    for (N, P, group) in [(10000, 32, 2), (50000, 256, 4), (200000, 2, 0)]:
+        feats = torch.randn(N, 768, device=dev)
+        cls = torch.nn.functional.normalize(torch.randn(768, P, device=dev), dim=0)
+        for tc in (True, False):
+            for _ in range(3):
+                ops.similarity(feats, cls, group=group, tensor_cores=tc)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                ops.similarity(feats, cls, group=group, tensor_cores=tc)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            byts = (N * 768 + 768 * P) * 4 + 2 * N * P * 4
+            print(f"[perf] similarity N={N} P={P} {'tf32-tcgen05' if tc else 'fp32-fma'}: {ms * 1e3:.1f} us = {byts / ms / 1e6:.0f} GB/s "
+                  f"(algorithmic bytes incl. logits+probs; includes the torch allocs of the wrapper)", flush=True)
+
+
 def probe_sim():
     def sim():
         feats = torch.randn(1000, 768, device=dev) * 2
@@ -275,6 +295,8 @@ if __name__ == "__main__":
         probe_sim()
     if "perf" in which and all(ok for n, ok in RESULTS if n.startswith("gemm")):
         run("perf", bench_gemm)
+    if "simperf" in which:
+        run("simperf", bench_similarity)
     if "attperf" in which:
         run("attperf", bench_attention)
     nfail = sum(1 for _, ok in RESULTS if not ok)
