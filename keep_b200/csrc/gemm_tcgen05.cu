@@ -85,7 +85,7 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int bf16) {
 
 // Drain one warp's share of an accumulator tile: TMEM lanes [32q, 32q+32) x columns [c_begin, c_end) of the
 // accumulator at `tmem_acc`; rows row0.. of the output, tile column base n0.
-template <int EPI>
+template <int EPI, bool LEAN = false>
 __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_acc, int q, int lane, int row0, int n0,
                                               int c_begin, int c_end, uint8_t* stage) {
   const uint32_t stage_addr = smem_u32(stage);
@@ -125,8 +125,10 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
         w.y = pack16(a.z, a.w, p.bf16);
         *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + (long long)r * p.ldo + col + tc) = w;
       } else if constexpr (EPI == EPI_RESID_F32) {
-        a.x = fmaf(g4.x, a.x, res[i].x); a.y = fmaf(g4.y, a.y, res[i].y);
-        a.z = fmaf(g4.z, a.z, res[i].z); a.w = fmaf(g4.w, a.w, res[i].w);
+        float4 rr = res[i];
+        if constexpr (LEAN) rr = *reinterpret_cast<const float4*>(p.resid + (long long)r * p.ldr + col + tc);
+        a.x = fmaf(g4.x, a.x, rr.x); a.y = fmaf(g4.y, a.y, rr.y);
+        a.z = fmaf(g4.z, a.z, rr.z); a.w = fmaf(g4.w, a.w, rr.w);
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + col + tc) = a;
       } else if constexpr (EPI == EPI_PATCH_F32) {
         const int img = r / p.patches, pi = r % p.patches;
@@ -141,7 +143,22 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
     __syncwarp();  // staging tile is rewritten by the next block
   };
 
-  if constexpr (EPI == EPI_RESID_F32) {
+  if constexpr (LEAN) {
+    // many-warp variant (16 epilogue warps): latency is hidden across warps, registers are kept low
+    const float4 none[8] = {};
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+      const int col = n0 + c0;
+      if (col >= p.N) break;
+      const float4 b4 = load_vec(p.bias, col, 0.f);
+      float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if constexpr (EPI == EPI_RESID_F32) g4 = load_vec(p.gamma, col, 1.f);
+      uint32_t v[32];
+      tmem_ld_32x32(t_lane + uint32_t(c0), v);
+      tmem_ld_wait();
+      process(v, none, col, b4, g4);
+    }
+  } else if constexpr (EPI == EPI_RESID_F32) {
 #pragma unroll 1
     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
       const int col = n0 + c0;
@@ -349,28 +366,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // ============================================================================================================
 // CTA-pair tiles (cta_group::2): 256 x 256 output tile per cluster of two CTAs
 // ============================================================================================================
+template <int EW>  // EW = number of epilogue warps (8: register-rich, pipelined; 16: lean, latency hidden across warps)
 struct Cfg2 {
   static constexpr int BN = 256;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;    // this CTA's 128 rows of A: 16 KB
   static constexpr int B_BYTES = (BN / 2) * BLOCK_K * 2;   // this CTA's 128 rows of W: 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB per CTA per stage
-  static constexpr int STAGES = 6;
+  static constexpr int STAGES = EW == 16 ? 5 : 6;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kEpiSmemBytes + BAR_BYTES + 1024;
+  static constexpr int EPI_BYTES = EW * kStageTileBytes;
+  static constexpr int THREADS = (kFirstEpiWarp + EW) * 32;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
 };
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+template <int EPI, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2<EW>::THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const KParams p) {
-  using C = Cfg2;
+  using C = Cfg2<EW>;
   constexpr int BN = C::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
   uint8_t* smem_epi = smem + C::STAGES * C::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiSmemBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + C::EPI_BYTES);
   uint64_t* full_bar = bars;                   // [STAGES] used in the leader CTA: bytes of BOTH CTAs land here
   uint64_t* empty_bar = bars + C::STAGES;      // [STAGES] per CTA, signalled by the leader's multicast commit
   uint64_t* tfull_bar = bars + 2 * C::STAGES;  // [2]      per CTA, multicast commit
@@ -398,7 +418,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 2 * kNumEpiWarps);
+      mbar_init(&tempty_bar[i], 2 * EW);
     }
     fence_mbar_init();
   }
@@ -460,7 +480,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   } else if (warp >= kFirstEpiWarp) {
     // ===================== epilogue (each CTA drains its own 128 rows) =====================
     const int q = warp & 3;
-    const int half = (warp - kFirstEpiWarp) >> 2;
+    constexpr int PARTS = EW / 4, PCOLS = BN / PARTS;  // column slices per lane quadrant
+    const int part = (warp - kFirstEpiWarp) >> 2;
     uint8_t* stage = smem_epi + (warp - kFirstEpiWarp) * kStageTileBytes;
     int lt = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++lt) {
@@ -471,12 +492,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         const int nt = tile + num_pairs;
         if (nt < num_tiles)
           prefetch_residual<EPI>(p, lane, (nt / n_tiles) * 2 * BLOCK_M + rank * BLOCK_M + q * 32,
-                                 (nt % n_tiles) * BN + half * (BN / 2), BN / 2);
+                                 (nt % n_tiles) * BN + part * PCOLS, PCOLS);
       }
       mbar_wait(&tfull_bar[as], aph, 14);
       tc_fence_after();
-      epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * 2 * BLOCK_M + rank * BLOCK_M + q * 32, n_blk * BN,
-                         half * (BN / 2), (half + 1) * (BN / 2), stage);
+      epilogue_warp<EPI, (EW == 16)>(p, tmem_base + as * BN, q, lane, m_blk * 2 * BLOCK_M + rank * BLOCK_M + q * 32,
+                                     n_blk * BN, part * PCOLS, (part + 1) * PCOLS, stage);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[as]), 0));
@@ -526,12 +547,24 @@ int launch_one(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, 
   return KB_OK;
 }
 
-template <int EPI>
-int launch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
-  using C = Cfg2;
+// epilogue-warp count per epilogue kind (KEEPB200_GEMM_EW=8|16 overrides for A/B measurements)
+int pair_epi_warps(int epi) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = std::getenv("KEEPB200_GEMM_EW");
+    forced = e ? std::atoi(e) : 0;
+  }
+  if (forced == 8 || forced == 16) return forced;
+  (void)epi;
+  return 8;  // measured: 16 lean warps are no faster (fc1) or slower (proj) than 8 pipelined ones
+}
+
+template <int EPI, int EW>
+int launch_pair_ew(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+  using C = Cfg2<EW>;
   static bool attr_set = false;
   if (!attr_set) {
-    KB_CUDA_CHECK(cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    KB_CUDA_CHECK(cudaFuncSetAttribute(gemm2_kernel<EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const KParams p = make_params(a, 2 * BLOCK_M, C::BN);
@@ -540,11 +573,16 @@ int launch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb,
   if (tiles < pairs) pairs = tiles;
   profile_gemm_tag(a.M, a.N, a.K, a.epi);
   profile_gemm_begin(stream);
-  gemm2_kernel<EPI><<<2 * pairs, kThreads, C::SMEM_BYTES, stream>>>(ta, tb, p);  // cluster dims are compile-time (2,1,1)
+  gemm2_kernel<EPI, EW><<<2 * pairs, C::THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);  // cluster dims are compile-time (2,1,1)
   profile_gemm_end(stream, 2.0 * a.M * a.N * a.K);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
+}
+
+template <int EPI>
+int launch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+  return pair_epi_warps(EPI) == 16 ? launch_pair_ew<EPI, 16>(a, ta, tb, stream) : launch_pair_ew<EPI, 8>(a, ta, tb, stream);
 }
 
 #define KB_DISPATCH_EPI(FN, ...)                                                             \

@@ -157,6 +157,27 @@ def probe_attention():
     run("att-bf16", lambda: case(2, 197, 16, False, torch.bfloat16))
 
 
+def bench_fc1_epilogues():
+    """Same GEMM (fc1 shape) with different epilogues: isolates the epilogue cost."""
+    M, N, K = 197 * 256, 4096, 1024
+    a = (torch.randn(M, K, device=dev) * 0.5).half()
+    w = (torch.randn(N, K, device=dev) * 0.05).half()
+    bias = torch.zeros(N, device=dev)
+    for epi, nm in ((0, "bias->fp16"), (1, "bias+gelu->fp16"), (3, "bias->fp32")):
+        out = None
+        for _ in range(3):
+            out = ops.gemm(a, w, epi, bias=bias, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.gemm(a, w, epi, bias=bias, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"[perf] fc1-shape epi={nm}: {ms:.3f} ms = {2.0 * M * N * K / ms / 1e9:.0f} TFLOP/s", flush=True)
+
+
 def bench_attention():
     for (B, S, H, masked) in [(512, 197, 16, False), (2048, 32, 12, True)]:
         qkv = torch.randn(B * S, 3 * H * 64, device=dev).half()
@@ -295,6 +316,8 @@ if __name__ == "__main__":
         probe_sim()
     if "perf" in which and all(ok for n, ok in RESULTS if n.startswith("gemm")):
         run("perf", bench_gemm)
+    if "epiperf" in which:
+        run("epiperf", bench_fc1_epilogues)
     if "simperf" in which:
         run("simperf", bench_similarity)
     if "attperf" in which:
