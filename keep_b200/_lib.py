@@ -6,6 +6,7 @@ toolkit is present and raises (loudly) otherwise; every wrapper raises `KeepB200
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 from . import build as _build
@@ -89,8 +90,9 @@ def lib() -> C.CDLL:
     if _LIB is not None:
         return _LIB
     path = _build.LIB_PATH
+    override = os.environ.get("KEEPB200_LIB")  # A/B measurements against another build of the same ABI
     try:
-        path = _build.build()
+        path = Path(override) if override else _build.build()
     except Exception as e:  # no toolkit on this box: fall through to a prebuilt in-tree library
         if not path.exists():
             raise KeepB200Error(

@@ -51,6 +51,7 @@ struct KParams {
   int patches;
   uint32_t idesc;
   int bf16;
+  int prefetch;  // residual epilogues: L2-prefetch the next tile's residual block (only pays when a tile is short)
 };
 
 // Exact-erf GELU (torch.nn.GELU() default), gelu(x) = x * Phi(x), written for the epilogue's instruction budget
@@ -84,19 +85,34 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int bf16) {
 }
 
 // Drain one warp's share of an accumulator tile: TMEM lanes [32q, 32q+32) x columns [c_begin, c_end) of the
-// accumulator at `tmem_acc`; rows row0.. of the output, tile column base n0.
-template <int EPI, bool LEAN = false>
+// accumulator at `tmem_acc`; rows row0.. of the output, tile column base n0. The warp waits for the accumulator
+// (`tfull`, `parity`) itself, AFTER it has issued the global loads that do not depend on it (bias, LayerScale, the
+// first residual block), so their DRAM latency hides behind the wait.
+template <int EPI>
 __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_acc, int q, int lane, int row0, int n0,
-                                              int c_begin, int c_end, uint8_t* stage) {
+                                              int c_begin, int c_end, uint8_t* stage, uint64_t* tfull, uint32_t parity,
+                                              int tag) {
   const uint32_t stage_addr = smem_u32(stage);
   // transposed role of this lane: rows 4i + (lane >> 3), columns 4*(lane & 7) .. +3 of the 32x32 block
   const int tr = lane >> 3, tc = (lane & 7) * 4;
   const uint32_t t_lane = tmem_acc + (uint32_t(q * 32) << 16);
+  int c_stop = c_end;
+  if (n0 + c_stop > p.N) c_stop = p.N - n0;  // N is a multiple of 32 (warp-uniform)
 
-  // one 32x32 block: accumulators of this lane's row in v[], `res` = prefetched residual (EPI_RESID_F32 only)
   auto load_vec = [&](const float* base, int col, float fill) {
     return base != nullptr ? __ldg(reinterpret_cast<const float4*>(base + col + tc)) : make_float4(fill, fill, fill, fill);
   };
+  auto load_res = [&](float4 (&res)[8], int col) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = row0 + 4 * i + tr;
+      res[i] = (r < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)r * p.ldr + col + tc)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  // One 32x32 block: accumulators of this lane's row in v[] -> warp-private staging tile -> row-contiguous role.
+  // The arithmetic of all 8 row groups is one straight-line block (32 independent chains: the GELU polynomial
+  // is latency-, not issue-bound), the guarded stores follow.
   auto process = [&](const uint32_t (&v)[32], const float4 (&res)[8], int col, float4 b4, float4 g4) {
     // own row `lane` -> staging, 16-byte chunk j at (j ^ (lane & 7)): conflict-free for both access patterns
 #pragma unroll
@@ -107,88 +123,112 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
                    : "memory");
     }
     __syncwarp();
+    if constexpr (EPI == EPI_BIAS_GELU_HALF) {
+      // row group by row group (load, GELU, store): measured 3% faster for this epilogue than the straight-line
+      // form below (A/B on one B200: fc1 1013 vs 983 TFLOP/s in the step), the stores drain under the next group's math
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rl = 4 * i + tr;
-      const int r = row0 + rl;
-      float4 a;
-      const uint32_t sa = stage_addr + rl * 128 + ((((lane & 7)) ^ (rl & 7)) << 4);
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(sa));
-      a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
-      if constexpr (EPI == EPI_BIAS_GELU_HALF) {
-        a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
-      }
-      if (r >= p.M) continue;
-      if constexpr (EPI == EPI_BIAS_HALF || EPI == EPI_BIAS_GELU_HALF) {
+      for (int i = 0; i < 8; ++i) {
+        const int rl = 4 * i + tr;
+        const int r = row0 + rl;
+        float4 a;
+        const uint32_t sa = stage_addr + rl * 128 + ((((lane & 7)) ^ (rl & 7)) << 4);
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(sa));
+        a.x = gelu_erf(a.x + b4.x); a.y = gelu_erf(a.y + b4.y); a.z = gelu_erf(a.z + b4.z); a.w = gelu_erf(a.w + b4.w);
+        if (r >= p.M) continue;
         uint2 w;
         w.x = pack16(a.x, a.y, p.bf16);
         w.y = pack16(a.z, a.w, p.bf16);
         *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + (long long)r * p.ldo + col + tc) = w;
-      } else if constexpr (EPI == EPI_RESID_F32) {
-        float4 rr = res[i];
-        if constexpr (LEAN) rr = *reinterpret_cast<const float4*>(p.resid + (long long)r * p.ldr + col + tc);
-        a.x = fmaf(g4.x, a.x, rr.x); a.y = fmaf(g4.y, a.y, rr.y);
-        a.z = fmaf(g4.z, a.z, rr.z); a.w = fmaf(g4.w, a.w, rr.w);
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + col + tc) = a;
-      } else if constexpr (EPI == EPI_PATCH_F32) {
-        const int img = r / p.patches, pi = r % p.patches;
-        const float4 p4 = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)(1 + pi) * p.N + col + tc));
-        a.x += p4.x; a.y += p4.y; a.z += p4.z; a.w += p4.w;
-        const long long orow = (long long)img * (p.patches + 1) + 1 + pi;
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col + tc) = a;
-      } else {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + col + tc) = a;
+      }
+      __syncwarp();  // staging tile is rewritten by the next block
+      return;
+    }
+    float4 a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = 4 * i + tr;
+      const uint32_t sa = stage_addr + rl * 128 + ((((lane & 7)) ^ (rl & 7)) << 4);
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a[i].x), "=f"(a[i].y), "=f"(a[i].z), "=f"(a[i].w) : "r"(sa));
+    }
+    __syncwarp();  // staging tile may be rewritten by the next block
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a[i].x += b4.x; a[i].y += b4.y; a[i].z += b4.z; a[i].w += b4.w;
+      if constexpr (EPI == EPI_BIAS_GELU_HALF) {
+        a[i].x = gelu_erf(a[i].x); a[i].y = gelu_erf(a[i].y); a[i].z = gelu_erf(a[i].z); a[i].w = gelu_erf(a[i].w);
+      }
+      if constexpr (EPI == EPI_RESID_F32) {
+        a[i].x = fmaf(g4.x, a[i].x, res[i].x); a[i].y = fmaf(g4.y, a[i].y, res[i].y);
+        a[i].z = fmaf(g4.z, a[i].z, res[i].z); a[i].w = fmaf(g4.w, a[i].w, res[i].w);
       }
     }
-    __syncwarp();  // staging tile is rewritten by the next block
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = row0 + 4 * i + tr;
+      if constexpr (EPI == EPI_BIAS_HALF || EPI == EPI_BIAS_GELU_HALF) {
+        uint2 w;
+        w.x = pack16(a[i].x, a[i].y, p.bf16);
+        w.y = pack16(a[i].z, a[i].w, p.bf16);
+        if (r < p.M) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + (long long)r * p.ldo + col + tc) = w;
+      } else if constexpr (EPI == EPI_PATCH_F32) {
+        if (r < p.M) {
+          const int img = r / p.patches, pi = r % p.patches;
+          const float4 p4 = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)(1 + pi) * p.N + col + tc));
+          float4 o = a[i];
+          o.x += p4.x; o.y += p4.y; o.z += p4.z; o.w += p4.w;
+          const long long orow = (long long)img * (p.patches + 1) + 1 + pi;
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col + tc) = o;
+        }
+      } else {
+        if (r < p.M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + col + tc) = a[i];
+      }
+    }
   };
 
-  if constexpr (LEAN) {
-    // many-warp variant (16 epilogue warps): latency is hidden across warps, registers are kept low
-    const float4 none[8] = {};
-#pragma unroll 1
-    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-      const int col = n0 + c0;
-      if (col >= p.N) break;
-      const float4 b4 = load_vec(p.bias, col, 0.f);
-      float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-      if constexpr (EPI == EPI_RESID_F32) g4 = load_vec(p.gamma, col, 1.f);
-      uint32_t v[32];
-      tmem_ld_32x32(t_lane + uint32_t(c0), v);
-      tmem_ld_wait();
-      process(v, none, col, b4, g4);
+  if constexpr (EPI == EPI_RESID_F32) {
+    // residual blocks are double-buffered: block c+1 is in flight (DRAM/L2 latency) while block c is transformed
+    float4 ra[8], rb[8];
+    float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba, ga = make_float4(1.f, 1.f, 1.f, 1.f), gb = ga;
+    if (c_begin < c_stop) {
+      load_res(ra, n0 + c_begin);
+      ba = load_vec(p.bias, n0 + c_begin, 0.f);
+      ga = load_vec(p.gamma, n0 + c_begin, 1.f);
     }
-  } else if constexpr (EPI == EPI_RESID_F32) {
+    mbar_wait(tfull, parity, tag);
+    tc_fence_after();
+    uint32_t v[32];
 #pragma unroll 1
-    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-      const int col = n0 + c0;
-      if (col >= p.N) break;  // warp-uniform; N is a multiple of 32
-      float4 res[8];
-      // issue the residual reads first: they do not depend on the accumulator
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = row0 + 4 * i + tr;
-        res[i] = (r < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)r * p.ldr + col + tc)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = c_begin; c0 < c_stop; c0 += 64) {
+      const bool has_b = c0 + 32 < c_stop;
+      if (has_b) {
+        load_res(rb, n0 + c0 + 32);
+        bb = load_vec(p.bias, n0 + c0 + 32, 0.f);
+        gb = load_vec(p.gamma, n0 + c0 + 32, 1.f);
       }
-      const float4 b4 = load_vec(p.bias, col, 0.f), g4 = load_vec(p.gamma, col, 1.f);
-      uint32_t v[32];
       tmem_ld_32x32(t_lane + uint32_t(c0), v);
-      tmem_ld_wait();
-      process(v, res, col, b4, g4);
+      tmem_ld_wait_dep(v);
+      process(v, ra, n0 + c0, ba, ga);
+      if (has_b) {
+        if (c0 + 64 < c_stop) {
+          load_res(ra, n0 + c0 + 64);
+          ba = load_vec(p.bias, n0 + c0 + 64, 0.f);
+          ga = load_vec(p.gamma, n0 + c0 + 64, 1.f);
+        }
+        tmem_ld_32x32(t_lane + uint32_t(c0 + 32), v);
+        tmem_ld_wait_dep(v);
+        process(v, rb, n0 + c0 + 32, bb, gb);
+      }
     }
   } else {
     // software-pipelined: the TMEM load of the next block is in flight while this one is transformed and stored
     const float4 none[8] = {};
     const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
     uint32_t va[32], vb[32];
-    int c_stop = c_end;
-    if (n0 + c_stop > p.N) c_stop = p.N - n0;  // N is a multiple of 32
     float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;  // bias of the block in flight, fetched with it
-    if (c_begin < c_stop) {
-      tmem_ld_32x32(t_lane + uint32_t(c_begin), va);
-      ba = load_vec(p.bias, n0 + c_begin, 0.f);
-    }
+    if (c_begin < c_stop) ba = load_vec(p.bias, n0 + c_begin, 0.f);
+    mbar_wait(tfull, parity, tag);
+    tc_fence_after();
+    if (c_begin < c_stop) tmem_ld_32x32(t_lane + uint32_t(c_begin), va);
 #pragma unroll 1
     for (int c0 = c_begin; c0 < c_stop; c0 += 64) {
       tmem_ld_wait_dep(va);
@@ -214,6 +254,7 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
 template <int EPI>
 __device__ __forceinline__ void prefetch_residual(const KParams& p, int lane, int row0, int col0, int ncols) {
   if constexpr (EPI == EPI_RESID_F32) {
+    if (!p.prefetch) return;
     // this warp's block: 32 rows x ncols fp32 = ncols/32 lines of 128 B per row
     const int lines_per_row = ncols >> 5;
     for (int i = lane; i < 32 * lines_per_row; i += 32) {
@@ -344,10 +385,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (nt < num_tiles)
           prefetch_residual<EPI>(p, lane, (nt / n_tiles) * BLOCK_M + q * 32, (nt % n_tiles) * BN + half * (BN / 2), BN / 2);
       }
-      mbar_wait(&tfull_bar[as], aph, 4);
-      tc_fence_after();
       epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * BLOCK_M + q * 32, n_blk * BN, half * (BN / 2),
-                         (half + 1) * (BN / 2), stage);
+                         (half + 1) * (BN / 2), stage, &tfull_bar[as], aph, 4);
       // all TMEM reads of this accumulator are complete (wait::ld): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -366,7 +405,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // ============================================================================================================
 // CTA-pair tiles (cta_group::2): 256 x 256 output tile per cluster of two CTAs
 // ============================================================================================================
-template <int EW>  // EW = number of epilogue warps (8: register-rich, pipelined; 16: lean, latency hidden across warps)
+template <int EW>  // EW = number of epilogue warps
 struct Cfg2 {
   static constexpr int BN = 256;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;    // this CTA's 128 rows of A: 16 KB
@@ -494,10 +533,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           prefetch_residual<EPI>(p, lane, (nt / n_tiles) * 2 * BLOCK_M + rank * BLOCK_M + q * 32,
                                  (nt % n_tiles) * BN + part * PCOLS, PCOLS);
       }
-      mbar_wait(&tfull_bar[as], aph, 14);
-      tc_fence_after();
-      epilogue_warp<EPI, (EW == 16)>(p, tmem_base + as * BN, q, lane, m_blk * 2 * BLOCK_M + rank * BLOCK_M + q * 32,
-                                     n_blk * BN, part * PCOLS, (part + 1) * PCOLS, stage);
+      epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * 2 * BLOCK_M + rank * BLOCK_M + q * 32, n_blk * BN,
+                         part * PCOLS, (part + 1) * PCOLS, stage, &tfull_bar[as], aph, 14);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[as]), 0));
@@ -523,6 +560,16 @@ KParams make_params(const GemmArgs& a, int umma_m, int umma_n) {
   p.out = a.out; p.ldo = a.ldo; p.pos = a.pos; p.patches = a.patches;
   p.idesc = make_idesc(a.bf16 ? kFmtBF16 : kFmtF16, umma_m, umma_n);
   p.bf16 = a.bf16;
+  // L2 prefetch of the next tile's residual block: off. With the first residual block requested before the accumulator
+  // wait and the blocks double-buffered it no longer pays (A/B on one B200: proj 906 vs 887 TFLOP/s without it), and
+  // a K=4096 tile streams ~4 MB per CTA pair through L2 first, so the prefetched lines were evicted again (ncu: +0.4 GB
+  // of DRAM reads per fc2 launch). KEEPB200_RESID_PREFETCH=1 re-enables it for measurements.
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = std::getenv("KEEPB200_RESID_PREFETCH");
+    forced = e ? std::atoi(e) : -1;
+  }
+  p.prefetch = forced >= 0 ? forced : 0;
   return p;
 }
 
@@ -545,18 +592,6 @@ int launch_one(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, 
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
-}
-
-// epilogue-warp count per epilogue kind (KEEPB200_GEMM_EW=8|16 overrides for A/B measurements)
-int pair_epi_warps(int epi) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = std::getenv("KEEPB200_GEMM_EW");
-    forced = e ? std::atoi(e) : 0;
-  }
-  if (forced == 8 || forced == 16) return forced;
-  (void)epi;
-  return 8;  // measured: 16 lean warps are no faster (fc1) or slower (proj) than 8 pipelined ones
 }
 
 template <int EPI, int EW>
@@ -582,7 +617,8 @@ int launch_pair_ew(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& 
 
 template <int EPI>
 int launch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
-  return pair_epi_warps(EPI) == 16 ? launch_pair_ew<EPI, 16>(a, ta, tb, stream) : launch_pair_ew<EPI, 8>(a, ta, tb, stream);
+  // 8 epilogue warps: a 16-warp variant (102 registers/thread) was measured no faster on fc1 and slower on proj
+  return launch_pair_ew<EPI, 8>(a, ta, tb, stream);
 }
 
 #define KB_DISPATCH_EPI(FN, ...)                                                             \
