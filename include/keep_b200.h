@@ -164,6 +164,18 @@ const char* keepb200_profile_table(void);
 int keepb200_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epi, int bf16,
                      const float* bias, const float* gamma, const float* resid, int64_t ldr, void* out, int64_t ldo,
                      const float* pos, int patches, void* stream);
+/* Fused LayerNorm across two GEMMs (the pre-LN ViT block, timm Block.forward: x + ls(attn(norm1(x))), x + ls(mlp(norm2(x)))).
+ *   op_gemm_resid_stats: x[M,N] += gamma * (A.W^T + bias); also x16 = 16-bit(x) and stats[M, N/64] = per-row (sum, sum of
+ *                        squares) over each 64-column slice of the NEW x
+ *   op_fold_ln:          W16 = 16-bit(W * lnw), s[n] = sum_k W16[n,k], c[n] = bias[n] + sum_k lnb[k] W[n,k]
+ *   op_gemm_ln:          out16 = act(rstd_r * (x16.W16^T - mean_r * s) + c) with mean/rstd from `stats` (K = width of x16,
+ *                        a multiple of 128); act = GELU(erf) when gelu != 0.  Equals act(Linear(LayerNorm(x))). */
+int keepb200_op_gemm_resid_stats(const void* A, const void* W, int M, int N, int K, int bf16, const float* bias,
+                                 const float* gamma, float* x, void* x16, float* stats, void* stream);
+int keepb200_op_gemm_ln(const void* x16, const void* Wf, int M, int N, int K, int gelu, int bf16, const float* c_vec,
+                        const float* s_vec, const float* stats, float eps, void* out16, void* stream);
+int keepb200_op_fold_ln(const float* W, int N, int K, const float* lnw, const float* lnb, const float* bias, void* W16,
+                        int bf16, float* s, float* c, void* stream);
 int keepb200_op_layernorm(const float* x, int64_t row_stride, int64_t rows, int D, const float* w, const float* b,
                           float eps, void* y16, int bf16, float* y32, void* stream);
 int keepb200_op_attention(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,

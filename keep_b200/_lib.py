@@ -71,6 +71,9 @@ SIGNATURES = {
     "keepb200_profile_end": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64)]),
     "keepb200_profile_table": (C.c_char_p, []),
     "keepb200_op_gemm": (_int, [_p, _i64, _p, _i64, _int, _int, _int, _int, _int, _p, _p, _p, _i64, _p, _i64, _p, _int, _p]),
+    "keepb200_op_gemm_resid_stats": (_int, [_p, _p, _int, _int, _int, _int, _p, _p, _p, _p, _p, _p]),
+    "keepb200_op_gemm_ln": (_int, [_p, _p, _int, _int, _int, _int, _int, _p, _p, _p, _f, _p, _p]),
+    "keepb200_op_fold_ln": (_int, [_p, _int, _int, _p, _p, _p, _p, _int, _p, _p, _p]),
     "keepb200_op_layernorm": (_int, [_p, _i64, _i64, _int, _p, _p, _f, _p, _int, _p, _p]),
     "keepb200_op_attention": (_int, [_p, _p, _int, _int, _int, _int, _p, _i64, _f, _p]),
     "keepb200_debug_attention_trace": (_int, [_p]),

@@ -5,6 +5,7 @@
 #include "common.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -22,11 +23,15 @@ struct WeightSlot {
   void* dst = nullptr;         // device destination (base of the owning allocation + offset)
   bool loaded = false;
   bool ignored = false;        // accepted but unused (logit_scale: dead at inference)
+  float* master = nullptr;     // fp32 copy kept for weights that are re-derived at finalize (LayerNorm folding)
 };
 
 struct VitBlock {
   float *n1w, *n1b, *qkv_b, *proj_b, *ls1, *n2w, *n2b, *fc1_b, *fc2_b, *ls2;
   void *qkv_w, *proj_w, *fc1_w, *fc2_w;
+  // LayerNorm folded into the following Linear (EPI_LN_*): 16-bit W * ln.weight, column sums, b.W^T + bias
+  void *qkv_wf = nullptr, *fc1_wf = nullptr;
+  float *qkv_s = nullptr, *qkv_c = nullptr, *fc1_s = nullptr, *fc1_c = nullptr;
 };
 struct BertLayer {
   void *qkv_w, *ao_w, *in_w, *out_w;
@@ -98,6 +103,19 @@ int new_w16(Model* m, const std::string& name, std::vector<int64_t> shape, void*
   return KB_OK;
 }
 
+// the slot registered last (a GEMM weight) also keeps an fp32 master and gets a LayerNorm-folded twin
+int add_fold(Model* m, size_t N, size_t K, void** wf, float** s_vec, float** c_vec) {
+  void* p;
+  KB_TRY(alloc_dev(m, N * K * 4, &p));
+  m->slots.back().master = static_cast<float*>(p);
+  KB_TRY(alloc_dev(m, N * K * 2, wf));
+  KB_TRY(alloc_dev(m, N * 4, &p));
+  *s_vec = static_cast<float*>(p);
+  KB_TRY(alloc_dev(m, N * 4, &p));
+  *c_vec = static_cast<float*>(p);
+  return KB_OK;
+}
+
 int build_tables(Model* m) {
   const KeepB200Config& c = m->cfg;
   const int D = c.vit_width, F = c.vit_mlp, T = m->tokens(), ps = c.patch_size;
@@ -113,6 +131,7 @@ int build_tables(Model* m) {
     KB_TRY(new_f32(m, p + "norm1.weight", {D}, &b.n1w));
     KB_TRY(new_f32(m, p + "norm1.bias", {D}, &b.n1b));
     KB_TRY(new_w16(m, p + "attn.qkv.weight", {3 * D, D}, &b.qkv_w));
+    KB_TRY(add_fold(m, (size_t)3 * D, D, &b.qkv_wf, &b.qkv_s, &b.qkv_c));
     KB_TRY(new_f32(m, p + "attn.qkv.bias", {3 * D}, &b.qkv_b));
     KB_TRY(new_w16(m, p + "attn.proj.weight", {D, D}, &b.proj_w));
     KB_TRY(new_f32(m, p + "attn.proj.bias", {D}, &b.proj_b));
@@ -120,6 +139,7 @@ int build_tables(Model* m) {
     KB_TRY(new_f32(m, p + "norm2.weight", {D}, &b.n2w));
     KB_TRY(new_f32(m, p + "norm2.bias", {D}, &b.n2b));
     KB_TRY(new_w16(m, p + "mlp.fc1.weight", {F, D}, &b.fc1_w));
+    KB_TRY(add_fold(m, (size_t)F, D, &b.fc1_wf, &b.fc1_s, &b.fc1_c));
     KB_TRY(new_f32(m, p + "mlp.fc1.bias", {F}, &b.fc1_b));
     KB_TRY(new_w16(m, p + "mlp.fc2.weight", {D, F}, &b.fc2_w));
     KB_TRY(new_f32(m, p + "mlp.fc2.bias", {D}, &b.fc2_b));
@@ -215,7 +235,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- workspace layouts -------------------------------------------------------------------------------------
 struct ImageWs {
-  size_t x, xn, qkv, att, hid, xc, cls16, h1, feat, total;
+  size_t x, xn, qkv, att, hid, xc, cls16, h1, feat, stats, total;
 };
 ImageWs image_ws(const Model* m, int64_t n) {
   const KeepB200Config& c = m->cfg;
@@ -236,6 +256,7 @@ ImageWs image_ws(const Model* m, int64_t n) {
   w.cls16 = take((size_t)n * D * 2);
   w.h1 = take((size_t)n * c.proj_dim * 2);
   w.feat = take((size_t)n * c.proj_dim * 4);
+  w.stats = take(M * (D / kLnSliceCols) * 8);  // LayerNorm partial sums of the residual rows (fused-LN path)
   w.total = off;
   return w;
 }
@@ -270,6 +291,33 @@ int gemm(const void* A, int64_t lda, const void* W, int M, int N, int K, int epi
   return launch_gemm(a, st);
 }
 
+// KEEPB200_LN_FUSE = 0: stand-alone LayerNorm kernels in every block; 1: norm1 fused (fc2 -> qkv); 2: norm1 and norm2
+// fused (also proj -> fc1). Read per call: tests flip it inside one process.
+int ln_fuse_mode() {
+  const char* e = std::getenv("KEEPB200_LN_FUSE");
+  if (e && e[0] >= '0' && e[0] <= '2') return e[0] - '0';
+  return 1;
+}
+
+// residual GEMM that also leaves the 16-bit copy of the new residual rows and their LayerNorm partial sums behind
+int gemm_resid_stats(const void* A, const void* W, int M, int N, int K, int bf16, const float* bias, const float* gamma,
+                     float* x, void* x16, float* stats, cudaStream_t st) {
+  GemmArgs a;
+  a.A = A; a.lda = K; a.W = W; a.ldw = K; a.M = M; a.N = N; a.K = K; a.epi = EPI_RESID_F32_STATS; a.bf16 = bf16;
+  a.bias = bias; a.gamma = gamma; a.resid = x; a.ldr = N; a.out = x; a.ldo = N; a.pos = nullptr; a.patches = 0;
+  a.out16 = x16; a.ldo16 = N; a.stats_out = stats;
+  return launch_gemm(a, st);
+}
+// GEMM on the un-normalised 16-bit residual copy with the LayerNorm folded into W / finished in the epilogue
+int gemm_ln(const void* x16, int D, const void* Wf, int M, int N, int epi, int bf16, const float* c_vec, const float* s_vec,
+            const float* stats, float eps, void* out, cudaStream_t st) {
+  GemmArgs a;
+  a.A = x16; a.lda = D; a.W = Wf; a.ldw = D; a.M = M; a.N = N; a.K = D; a.epi = epi; a.bf16 = bf16;
+  a.bias = c_vec; a.gamma = nullptr; a.resid = nullptr; a.ldr = 0; a.out = out; a.ldo = N; a.pos = nullptr; a.patches = 0;
+  a.ln_stats = stats; a.ln_slices = D / kLnSliceCols; a.ln_width = D; a.ln_eps = eps; a.ln_s = s_vec;
+  return launch_gemm(a, st);
+}
+
 int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, float* out, char* ws, cudaStream_t st) {
   const KeepB200Config& c = m->cfg;
   const int bf = c.operand_dtype, D = c.vit_width, F = c.vit_mlp, T = m->tokens(), G = m->grid();
@@ -284,6 +332,11 @@ int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, float
   void* cls16 = ws + w.cls16;
   void* h1 = ws + w.h1;
   float* feat = reinterpret_cast<float*>(ws + w.feat);
+  float* stats = reinterpret_cast<float*>(ws + w.stats);
+  // Fused LayerNorm (default): proj / fc2 leave 16-bit(x) in `xn` plus per-row partial sums, and fc1 / the next
+  // block's qkv run on it with the LayerNorm folded in (EPI_LN_*). Only norm1 of block 0 (x comes from the patch
+  // embedding) and the CLS-row tail of the last block use the stand-alone kernel.
+  const int fuse = ln_fuse_mode();
 
   // patch gather (+ CLS rows), then patch-embed GEMM scattering into x[b, 1+p, :] with +bias +pos
   if (layout == KEEPB200_TILES_F32_NCHW)
@@ -294,10 +347,25 @@ int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, float
               m->pos, T - 1));
   for (int i = 0; i < c.vit_depth; ++i) {
     const VitBlock& b = m->blocks[i];
-    KB_TRY(launch_layernorm(x, D, M, D, b.n1w, b.n1b, c.vit_ln_eps, xn, bf, nullptr, st));
-    KB_TRY(gemm(xn, D, b.qkv_w, M, 3 * D, D, EPI_BIAS_HALF, bf, b.qkv_b, nullptr, nullptr, qkv, 3 * D, st));
+    if (fuse >= 1 && i > 0) {
+      KB_TRY(gemm_ln(xn, D, b.qkv_wf, M, 3 * D, EPI_LN_BIAS_HALF, bf, b.qkv_c, b.qkv_s, stats, c.vit_ln_eps, qkv, st));
+    } else {
+      KB_TRY(launch_layernorm(x, D, M, D, b.n1w, b.n1b, c.vit_ln_eps, xn, bf, nullptr, st));
+      KB_TRY(gemm(xn, D, b.qkv_w, M, 3 * D, D, EPI_BIAS_HALF, bf, b.qkv_b, nullptr, nullptr, qkv, 3 * D, st));
+    }
     KB_TRY(launch_attention(qkv, att, (int)n, T, c.vit_heads, bf, nullptr, 0, 0.125f, st));
-    if (i + 1 < c.vit_depth) {
+    if (i + 1 < c.vit_depth && fuse == 2) {
+      KB_TRY(gemm_resid_stats(att, b.proj_w, M, D, D, bf, b.proj_b, b.ls1, x, xn, stats, st));
+      KB_TRY(gemm_ln(xn, D, b.fc1_wf, M, F, EPI_LN_BIAS_GELU_HALF, bf, b.fc1_c, b.fc1_s, stats, c.vit_ln_eps, hid, st));
+      KB_TRY(gemm_resid_stats(hid, b.fc2_w, M, D, F, bf, b.fc2_b, b.ls2, x, xn, stats, st));
+    } else if (i + 1 < c.vit_depth && fuse == 1) {
+      // proj is HBM-bound (fp32 residual read-modify-write): the extra 16-bit copy costs it what the LayerNorm kernel
+      // costs, so norm2 stays a kernel; fc2 (K = 4096, compute-bound) emits the copy and the statistics for free
+      KB_TRY(gemm(att, D, b.proj_w, M, D, D, EPI_RESID_F32, bf, b.proj_b, b.ls1, x, x, D, st));
+      KB_TRY(launch_layernorm(x, D, M, D, b.n2w, b.n2b, c.vit_ln_eps, xn, bf, nullptr, st));
+      KB_TRY(gemm(xn, D, b.fc1_w, M, F, D, EPI_BIAS_GELU_HALF, bf, b.fc1_b, nullptr, nullptr, hid, F, st));
+      KB_TRY(gemm_resid_stats(hid, b.fc2_w, M, D, F, bf, b.fc2_b, b.ls2, x, xn, stats, st));
+    } else if (i + 1 < c.vit_depth) {
       KB_TRY(gemm(att, D, b.proj_w, M, D, D, EPI_RESID_F32, bf, b.proj_b, b.ls1, x, x, D, st));
       KB_TRY(launch_layernorm(x, D, M, D, b.n2w, b.n2b, c.vit_ln_eps, xn, bf, nullptr, st));
       KB_TRY(gemm(xn, D, b.fc1_w, M, F, D, EPI_BIAS_GELU_HALF, bf, b.fc1_b, nullptr, nullptr, hid, F, st));
@@ -441,6 +509,7 @@ int keepb200_load_weight(void* handle, const char* name, const float* data, cons
   size_t n = 1;
   for (auto d : s.shape) n *= (size_t)d;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (s.master != nullptr) KB_CUDA_CHECK(cudaMemcpyAsync(s.master, data, n * 4, cudaMemcpyDeviceToDevice, st));
   if (s.as16)
     KB_TRY(launch_cast_f32_to_16(data, s.dst, (int64_t)n, m->cfg.operand_dtype, st));
   else
@@ -461,6 +530,22 @@ int keepb200_finalize(void* handle) {
       ++count;
     }
   if (count) return set_error(KB_ERR_STATE, "finalize: %d missing key(s): %s%s", count, missing.c_str(), count > 4 ? "..." : "");
+  // derive the LayerNorm-folded operands (norm1 -> qkv, norm2 -> fc1) from the fp32 masters; the weights were copied
+  // on caller streams, so fence the device on both sides
+  KB_CUDA_CHECK(cudaDeviceSynchronize());
+  {
+    const KeepB200Config& c = m->cfg;
+    const int D = c.vit_width, F = c.vit_mlp, bf = c.operand_dtype;
+    for (int i = 0; i < c.vit_depth; ++i) {
+      VitBlock& b = m->blocks[i];
+      const std::string p = "visual.blocks." + std::to_string(i) + ".";
+      const float* qkv32 = m->slots[m->index[p + "attn.qkv.weight"]].master;
+      const float* fc132 = m->slots[m->index[p + "mlp.fc1.weight"]].master;
+      KB_TRY(launch_fold_ln(qkv32, 3 * D, D, b.n1w, b.n1b, b.qkv_b, b.qkv_wf, bf, b.qkv_s, b.qkv_c, nullptr));
+      KB_TRY(launch_fold_ln(fc132, F, D, b.n2w, b.n2b, b.fc1_b, b.fc1_wf, bf, b.fc1_s, b.fc1_c, nullptr));
+    }
+  }
+  KB_CUDA_CHECK(cudaDeviceSynchronize());
   m->finalized = true;
   return KB_OK;
 }
@@ -613,6 +698,20 @@ int keepb200_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int
   a.bias = bias; a.gamma = gamma; a.resid = resid; a.ldr = ldr; a.out = out; a.ldo = ldo; a.pos = pos;
   a.patches = patches;
   return launch_gemm(a, static_cast<cudaStream_t>(stream));
+}
+int keepb200_op_gemm_resid_stats(const void* A, const void* W, int M, int N, int K, int bf16, const float* bias,
+                                 const float* gamma, float* x, void* x16, float* stats, void* stream) {
+  return gemm_resid_stats(A, W, M, N, K, bf16, bias, gamma, x, x16, stats, static_cast<cudaStream_t>(stream));
+}
+int keepb200_op_gemm_ln(const void* x16, const void* Wf, int M, int N, int K, int gelu, int bf16, const float* c_vec,
+                        const float* s_vec, const float* stats, float eps, void* out16, void* stream) {
+  if (K % (2 * kLnSliceCols) != 0) return set_error(KB_ERR_ARG, "op_gemm_ln: K=%d must be a multiple of %d", K, 2 * kLnSliceCols);
+  return gemm_ln(x16, K, Wf, M, N, gelu ? EPI_LN_BIAS_GELU_HALF : EPI_LN_BIAS_HALF, bf16, c_vec, s_vec, stats, eps, out16,
+                 static_cast<cudaStream_t>(stream));
+}
+int keepb200_op_fold_ln(const float* W, int N, int K, const float* lnw, const float* lnb, const float* bias, void* W16,
+                        int bf16, float* s, float* c, void* stream) {
+  return launch_fold_ln(W, N, K, lnw, lnb, bias, W16, bf16, s, c, static_cast<cudaStream_t>(stream));
 }
 int keepb200_op_layernorm(const float* x, int64_t row_stride, int64_t rows, int D, const float* w, const float* b,
                           float eps, void* y16, int bf16, float* y32, void* stream) {

@@ -53,8 +53,15 @@ enum : int {
   EPI_BIAS_GELU_HALF = 1,  // out16[r,c] = gelu_erf(acc + bias[c])
   EPI_RESID_F32 = 2,       // out32[r,c] = resid[r,c] + gamma[c] * (acc + bias[c])   (gamma may be null => 1)
   EPI_BIAS_F32 = 3,        // out32[r,c] = acc + bias[c]
-  EPI_PATCH_F32 = 4        // out32[(r/P)*(P+1)+1+r%P, c] = acc + bias[c] + pos[1+r%P, c]   (ViT patch embed)
+  EPI_PATCH_F32 = 4,       // out32[(r/P)*(P+1)+1+r%P, c] = acc + bias[c] + pos[1+r%P, c]   (ViT patch embed)
+  // LayerNorm fused across two GEMMs (the pre-LN ViT block): the residual GEMM also emits the 16-bit
+  // copy of the new residual row and per-row partial sums; the next GEMM runs on that copy with the LayerNorm scale
+  // folded into its weights (launch_fold_ln) and finishes the normalisation per output row in its epilogue.
+  EPI_RESID_F32_STATS = 5,   // EPI_RESID_F32 + out16[r,c] = 16-bit(out32[r,c]); stats[r, c/64] = (sum, sum of squares)
+  EPI_LN_BIAS_HALF = 6,      // out16[r,c] = rstd_r * (acc - mean_r * ln_s[c]) + bias[c]
+  EPI_LN_BIAS_GELU_HALF = 7  // out16[r,c] = gelu_erf(rstd_r * (acc - mean_r * ln_s[c]) + bias[c])
 };
+constexpr int kLnSliceCols = 64;  // width of one partial-sum slice of the row statistics
 struct GemmArgs {
   const void* A;  int64_t lda;   // [M,K] 16-bit, K contiguous
   const void* W;  int64_t ldw;   // [N,K] 16-bit, K contiguous (torch Linear weight)
@@ -66,6 +73,12 @@ struct GemmArgs {
   const float* resid; int64_t ldr;
   void* out; int64_t ldo;
   const float* pos; int patches; // EPI_PATCH_F32 only
+  // EPI_RESID_F32_STATS (producer): 16-bit copy + row statistics [M, N/64] float2
+  void* out16 = nullptr; int64_t ldo16 = 0;
+  float* stats_out = nullptr;
+  // EPI_LN_* (consumer): statistics of the A rows ([M, ln_slices] float2 over ln_width columns), folded column sums
+  const float* ln_stats = nullptr; int ln_slices = 0; int ln_width = 0; float ln_eps = 0.f;
+  const float* ln_s = nullptr;   // [N]  sum_k W'[n,k]   (bias carries b.W^T + bias)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 
@@ -119,6 +132,11 @@ int launch_scale(float* v, int64_t n, float s, cudaStream_t stream);
 size_t refine_workspace_bytes(int64_t N);
 int launch_refine(const int64_t* coords, const float* probs, int64_t N, int C, int64_t ps, int overlap, uint8_t* keep,
                   float* refined, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// LayerNorm folding for EPI_LN_*: W'[n,k] = 16-bit(W[n,k] * lnw[k]); s[n] = sum_k W'[n,k] (of the ROUNDED values: it
+// cancels against what the tensor core accumulates); c[n] = bias[n] + sum_k lnb[k] * W[n,k]
+int launch_fold_ln(const float* W, int N, int K, const float* lnw, const float* lnb, const float* bias, void* W16,
+                   int bf16, float* s, float* c, cudaStream_t stream);
 
 // generic helpers
 int launch_cast_f32_to_16(const float* src, void* dst, int64_t n, int bf16, cudaStream_t stream);

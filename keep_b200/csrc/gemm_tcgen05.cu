@@ -51,6 +51,13 @@ struct KParams {
   int patches;
   uint32_t idesc;
   int bf16;
+  uint16_t* out16;       // EPI_RESID_F32_STATS: 16-bit copy of the output
+  long long ldo16;
+  float* stats_out;      // EPI_RESID_F32_STATS: [M, N/64] (sum, sum of squares)
+  const float* ln_stats; // EPI_LN_*: [M, ln_slices] (sum, sum of squares) of the A rows
+  const float* ln_s;     // EPI_LN_*: [N] column sums of the folded weight
+  int ln_slices;
+  float ln_inv_width, ln_eps;
   int prefetch;  // residual epilogues: L2-prefetch the next tile's residual block (only pays when a tile is short)
 };
 
@@ -84,14 +91,23 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int bf16) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+template <int EPI> struct EpiTraits {
+  static constexpr bool kResid = (EPI == EPI_RESID_F32 || EPI == EPI_RESID_F32_STATS);
+  static constexpr bool kStats = (EPI == EPI_RESID_F32_STATS);
+  static constexpr bool kLn = (EPI == EPI_LN_BIAS_HALF || EPI == EPI_LN_BIAS_GELU_HALF);
+  static constexpr bool kGelu = (EPI == EPI_BIAS_GELU_HALF || EPI == EPI_LN_BIAS_GELU_HALF);
+  static constexpr bool kHalfOut = (EPI == EPI_BIAS_HALF || EPI == EPI_BIAS_GELU_HALF || kLn);
+};
+
 // Drain one warp's share of an accumulator tile: TMEM lanes [32q, 32q+32) x columns [c_begin, c_end) of the
 // accumulator at `tmem_acc`; rows row0.. of the output, tile column base n0. The warp waits for the accumulator
 // (`tfull`, `parity`) itself, AFTER it has issued the global loads that do not depend on it (bias, LayerScale, the
-// first residual block), so their DRAM latency hides behind the wait.
+// first residual block, the LayerNorm statistics of its rows), so their DRAM latency hides behind the wait.
 template <int EPI>
 __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_acc, int q, int lane, int row0, int n0,
                                               int c_begin, int c_end, uint8_t* stage, uint64_t* tfull, uint32_t parity,
                                               int tag) {
+  using T = EpiTraits<EPI>;
   const uint32_t stage_addr = smem_u32(stage);
   // transposed role of this lane: rows 4i + (lane >> 3), columns 4*(lane & 7) .. +3 of the 32x32 block
   const int tr = lane >> 3, tc = (lane & 7) * 4;
@@ -110,9 +126,31 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
                          : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
+
+  // EPI_LN_*: LayerNorm statistics of row (row0 + lane) of A, from the partial sums the producing GEMM left behind;
+  // the transposed role fetches the pair of the row it is working on with two shuffles
+  float ln_nmu = 0.f, ln_rstd = 0.f;
+  if constexpr (T::kLn) {
+    const int r = row0 + lane;
+    if (r < p.M) {
+      const float4* st = reinterpret_cast<const float4*>(p.ln_stats + (long long)r * p.ln_slices * 2);
+      float sum = 0.f, sq = 0.f;
+      for (int j = 0; j < p.ln_slices / 2; ++j) {  // fixed order: deterministic
+        const float4 t = st[j];
+        sum += t.x + t.z;
+        sq += t.y + t.w;
+      }
+      const float mean = sum * p.ln_inv_width;
+      const float var = fmaxf(fmaf(sq, p.ln_inv_width, -mean * mean), 0.f);
+      ln_rstd = 1.0f / sqrtf(var + p.ln_eps);
+      ln_nmu = -mean;
+    }
+  }
+  // EPI_RESID_F32_STATS: per-lane partial sums of the new residual rows over the current 64-column slice
+  float st_s[8], st_q[8];
+
   // One 32x32 block: accumulators of this lane's row in v[] -> warp-private staging tile -> row-contiguous role.
-  // The arithmetic of all 8 row groups is one straight-line block (32 independent chains: the GELU polynomial
-  // is latency-, not issue-bound), the guarded stores follow.
+  // g4 = LayerScale (residual epilogues) or the folded column sums ln_s (EPI_LN_*).
   auto process = [&](const uint32_t (&v)[32], const float4 (&res)[8], int col, float4 b4, float4 g4) {
     // own row `lane` -> staging, 16-byte chunk j at (j ^ (lane & 7)): conflict-free for both access patterns
 #pragma unroll
@@ -123,7 +161,7 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
                    : "memory");
     }
     __syncwarp();
-    if constexpr (EPI == EPI_BIAS_GELU_HALF) {
+    if constexpr (T::kGelu) {
       // row group by row group (load, GELU, store): measured 3% faster for this epilogue than the straight-line
       // form below (A/B on one B200: fc1 1013 vs 983 TFLOP/s in the step), the stores drain under the next group's math
 #pragma unroll
@@ -133,7 +171,14 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
         float4 a;
         const uint32_t sa = stage_addr + rl * 128 + ((((lane & 7)) ^ (rl & 7)) << 4);
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(sa));
-        a.x = gelu_erf(a.x + b4.x); a.y = gelu_erf(a.y + b4.y); a.z = gelu_erf(a.z + b4.z); a.w = gelu_erf(a.w + b4.w);
+        if constexpr (T::kLn) {
+          const float nm = __shfl_sync(0xffffffffu, ln_nmu, rl), rs = __shfl_sync(0xffffffffu, ln_rstd, rl);
+          a.x = fmaf(rs, fmaf(nm, g4.x, a.x), b4.x); a.y = fmaf(rs, fmaf(nm, g4.y, a.y), b4.y);
+          a.z = fmaf(rs, fmaf(nm, g4.z, a.z), b4.z); a.w = fmaf(rs, fmaf(nm, g4.w, a.w), b4.w);
+        } else {
+          a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+        }
+        a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
         if (r >= p.M) continue;
         uint2 w;
         w.x = pack16(a.x, a.y, p.bf16);
@@ -143,6 +188,7 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
       __syncwarp();  // staging tile is rewritten by the next block
       return;
     }
+    // straight-line form: the arithmetic of all 8 row groups is one basic block, the guarded stores follow
     float4 a[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -153,19 +199,26 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
     __syncwarp();  // staging tile may be rewritten by the next block
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      a[i].x += b4.x; a[i].y += b4.y; a[i].z += b4.z; a[i].w += b4.w;
-      if constexpr (EPI == EPI_BIAS_GELU_HALF) {
-        a[i].x = gelu_erf(a[i].x); a[i].y = gelu_erf(a[i].y); a[i].z = gelu_erf(a[i].z); a[i].w = gelu_erf(a[i].w);
+      if constexpr (T::kLn) {
+        const float nm = __shfl_sync(0xffffffffu, ln_nmu, 4 * i + tr), rs = __shfl_sync(0xffffffffu, ln_rstd, 4 * i + tr);
+        a[i].x = fmaf(rs, fmaf(nm, g4.x, a[i].x), b4.x); a[i].y = fmaf(rs, fmaf(nm, g4.y, a[i].y), b4.y);
+        a[i].z = fmaf(rs, fmaf(nm, g4.z, a[i].z), b4.z); a[i].w = fmaf(rs, fmaf(nm, g4.w, a[i].w), b4.w);
+      } else {
+        a[i].x += b4.x; a[i].y += b4.y; a[i].z += b4.z; a[i].w += b4.w;
       }
-      if constexpr (EPI == EPI_RESID_F32) {
+      if constexpr (T::kResid) {
         a[i].x = fmaf(g4.x, a[i].x, res[i].x); a[i].y = fmaf(g4.y, a[i].y, res[i].y);
         a[i].z = fmaf(g4.z, a[i].z, res[i].z); a[i].w = fmaf(g4.w, a[i].w, res[i].w);
+      }
+      if constexpr (T::kStats) {
+        st_s[i] += (a[i].x + a[i].y) + (a[i].z + a[i].w);
+        st_q[i] = fmaf(a[i].x, a[i].x, fmaf(a[i].y, a[i].y, fmaf(a[i].z, a[i].z, fmaf(a[i].w, a[i].w, st_q[i]))));
       }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = row0 + 4 * i + tr;
-      if constexpr (EPI == EPI_BIAS_HALF || EPI == EPI_BIAS_GELU_HALF) {
+      if constexpr (T::kHalfOut) {
         uint2 w;
         w.x = pack16(a[i].x, a[i].y, p.bf16);
         w.y = pack16(a[i].z, a[i].w, p.bf16);
@@ -181,11 +234,47 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
         }
       } else {
         if (r < p.M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + col + tc) = a[i];
+        if constexpr (T::kStats) {
+          uint2 w;
+          w.x = pack16(a[i].x, a[i].y, p.bf16);
+          w.y = pack16(a[i].z, a[i].w, p.bf16);
+          if (r < p.M) *reinterpret_cast<uint2*>(p.out16 + (long long)r * p.ldo16 + col + tc) = w;
+        }
       }
     }
   };
+  // EPI_RESID_F32_STATS: fold the per-lane partials of one 64-column slice across the 8 lanes that share a row
+  // (exchange-and-add butterfly: 14 shuffles; lane j of a row group ends up with the totals of row 4j + tr) and
+  // store them as stats[row, slice] = (sum, sum of squares)
+  auto flush_stats = [&](int col64) {
+    if constexpr (T::kStats) {
+      const bool b4 = (lane & 4) != 0, b2 = (lane & 2) != 0, b1 = (lane & 1) != 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float ks = b4 ? st_s[k + 4] : st_s[k], ss = b4 ? st_s[k] : st_s[k + 4];
+        const float kq = b4 ? st_q[k + 4] : st_q[k], sq = b4 ? st_q[k] : st_q[k + 4];
+        st_s[k] = ks + __shfl_xor_sync(0xffffffffu, ss, 4);
+        st_q[k] = kq + __shfl_xor_sync(0xffffffffu, sq, 4);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float ks = b2 ? st_s[k + 2] : st_s[k], ss = b2 ? st_s[k] : st_s[k + 2];
+        const float kq = b2 ? st_q[k + 2] : st_q[k], sq = b2 ? st_q[k] : st_q[k + 2];
+        st_s[k] = ks + __shfl_xor_sync(0xffffffffu, ss, 2);
+        st_q[k] = kq + __shfl_xor_sync(0xffffffffu, sq, 2);
+      }
+      const float ks = b1 ? st_s[1] : st_s[0], ss = b1 ? st_s[0] : st_s[1];
+      const float kq = b1 ? st_q[1] : st_q[0], sq = b1 ? st_q[0] : st_q[1];
+      const float tot_s = ks + __shfl_xor_sync(0xffffffffu, ss, 1);
+      const float tot_q = kq + __shfl_xor_sync(0xffffffffu, sq, 1);
+      const int r = row0 + 4 * (lane & 7) + tr;
+      if (r < p.M)
+        *reinterpret_cast<float2*>(p.stats_out + ((long long)r * (p.N / kLnSliceCols) + col64 / kLnSliceCols) * 2) =
+            make_float2(tot_s, tot_q);
+    }
+  };
 
-  if constexpr (EPI == EPI_RESID_F32) {
+  if constexpr (T::kResid) {
     // residual blocks are double-buffered: block c+1 is in flight (DRAM/L2 latency) while block c is transformed
     float4 ra[8], rb[8];
     float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba, ga = make_float4(1.f, 1.f, 1.f, 1.f), gb = ga;
@@ -200,6 +289,10 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
 #pragma unroll 1
     for (int c0 = c_begin; c0 < c_stop; c0 += 64) {
       const bool has_b = c0 + 32 < c_stop;
+      if constexpr (T::kStats) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st_s[i] = st_q[i] = 0.f;
+      }
       if (has_b) {
         load_res(rb, n0 + c0 + 32);
         bb = load_vec(p.bias, n0 + c0 + 32, 0.f);
@@ -218,14 +311,19 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
         tmem_ld_wait_dep(v);
         process(v, rb, n0 + c0 + 32, bb, gb);
       }
+      flush_stats(n0 + c0);  // N % 64 == 0 is checked at launch for this epilogue
     }
   } else {
     // software-pipelined: the TMEM load of the next block is in flight while this one is transformed and stored
     const float4 none[8] = {};
-    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+    const float* gvec = T::kLn ? p.ln_s : nullptr;
     uint32_t va[32], vb[32];
     float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bb = ba;  // bias of the block in flight, fetched with it
-    if (c_begin < c_stop) ba = load_vec(p.bias, n0 + c_begin, 0.f);
+    float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), gb = ga;
+    if (c_begin < c_stop) {
+      ba = load_vec(p.bias, n0 + c_begin, 0.f);
+      if constexpr (T::kLn) ga = load_vec(gvec, n0 + c_begin, 0.f);
+    }
     mbar_wait(tfull, parity, tag);
     tc_fence_after();
     if (c_begin < c_stop) tmem_ld_32x32(t_lane + uint32_t(c_begin), va);
@@ -235,15 +333,17 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
       if (c0 + 32 < c_stop) {
         tmem_ld_32x32(t_lane + uint32_t(c0 + 32), vb);
         bb = load_vec(p.bias, n0 + c0 + 32, 0.f);
+        if constexpr (T::kLn) gb = load_vec(gvec, n0 + c0 + 32, 0.f);
       }
-      process(va, none, n0 + c0, ba, one);
+      process(va, none, n0 + c0, ba, ga);
       if (c0 + 32 < c_stop) {
         tmem_ld_wait_dep(vb);
         if (c0 + 64 < c_stop) {
           tmem_ld_32x32(t_lane + uint32_t(c0 + 64), va);
           ba = load_vec(p.bias, n0 + c0 + 64, 0.f);
+          if constexpr (T::kLn) ga = load_vec(gvec, n0 + c0 + 64, 0.f);
         }
-        process(vb, none, n0 + c0 + 32, bb, one);
+        process(vb, none, n0 + c0 + 32, bb, gb);
       }
     }
   }
@@ -253,7 +353,7 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
 // tile i is being drained, so that the epilogue's loads hit L2 instead of paying the DRAM latency per 32x32 block.
 template <int EPI>
 __device__ __forceinline__ void prefetch_residual(const KParams& p, int lane, int row0, int col0, int ncols) {
-  if constexpr (EPI == EPI_RESID_F32) {
+  if constexpr (EpiTraits<EPI>::kResid) {
     if (!p.prefetch) return;
     // this warp's block: 32 rows x ncols fp32 = ncols/32 lines of 128 B per row
     const int lines_per_row = ncols >> 5;
@@ -560,6 +660,9 @@ KParams make_params(const GemmArgs& a, int umma_m, int umma_n) {
   p.out = a.out; p.ldo = a.ldo; p.pos = a.pos; p.patches = a.patches;
   p.idesc = make_idesc(a.bf16 ? kFmtBF16 : kFmtF16, umma_m, umma_n);
   p.bf16 = a.bf16;
+  p.out16 = static_cast<uint16_t*>(a.out16); p.ldo16 = a.ldo16; p.stats_out = a.stats_out;
+  p.ln_stats = a.ln_stats; p.ln_s = a.ln_s; p.ln_slices = a.ln_slices;
+  p.ln_inv_width = a.ln_width > 0 ? 1.0f / (float)a.ln_width : 0.f; p.ln_eps = a.ln_eps;
   // L2 prefetch of the next tile's residual block: off. With the first residual block requested before the accumulator
   // wait and the blocks double-buffered it no longer pays (A/B on one B200: proj 906 vs 887 TFLOP/s without it), and
   // a K=4096 tile streams ~4 MB per CTA pair through L2 first, so the prefetched lines were evicted again (ncu: +0.4 GB
@@ -628,6 +731,9 @@ int launch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb,
     case EPI_RESID_F32: return FN<__VA_ARGS__ EPI_RESID_F32>(a, ta, tb, stream);             \
     case EPI_BIAS_F32: return FN<__VA_ARGS__ EPI_BIAS_F32>(a, ta, tb, stream);               \
     case EPI_PATCH_F32: return FN<__VA_ARGS__ EPI_PATCH_F32>(a, ta, tb, stream);             \
+    case EPI_RESID_F32_STATS: return FN<__VA_ARGS__ EPI_RESID_F32_STATS>(a, ta, tb, stream); \
+    case EPI_LN_BIAS_HALF: return FN<__VA_ARGS__ EPI_LN_BIAS_HALF>(a, ta, tb, stream);       \
+    case EPI_LN_BIAS_GELU_HALF: return FN<__VA_ARGS__ EPI_LN_BIAS_GELU_HALF>(a, ta, tb, stream); \
     default: return set_error(KB_ERR_ARG, "gemm: unknown epilogue %d", a.epi);               \
   }
 
@@ -660,7 +766,13 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return set_error(KB_ERR_ARG, "gemm: empty problem %dx%dx%d", a.M, a.N, a.K);
   if (a.K % BLOCK_K != 0) return set_error(KB_ERR_ARG, "gemm: K=%d must be a multiple of %d", a.K, BLOCK_K);
   if (a.N % 32 != 0) return set_error(KB_ERR_ARG, "gemm: N=%d must be a multiple of 32", a.N);
-  if (a.epi == EPI_RESID_F32 && a.resid == nullptr) return set_error(KB_ERR_ARG, "gemm: residual epilogue without resid");
+  if ((a.epi == EPI_RESID_F32 || a.epi == EPI_RESID_F32_STATS) && a.resid == nullptr)
+    return set_error(KB_ERR_ARG, "gemm: residual epilogue without resid");
+  if (a.epi == EPI_RESID_F32_STATS && (a.out16 == nullptr || a.stats_out == nullptr || a.N % kLnSliceCols != 0))
+    return set_error(KB_ERR_ARG, "gemm: stats epilogue needs out16, stats_out and N %% %d == 0 (N=%d)", kLnSliceCols, a.N);
+  if ((a.epi == EPI_LN_BIAS_HALF || a.epi == EPI_LN_BIAS_GELU_HALF) &&
+      (a.ln_stats == nullptr || a.ln_s == nullptr || a.ln_slices <= 0 || a.ln_slices % 2 != 0 || a.ln_width <= 0))
+    return set_error(KB_ERR_ARG, "gemm: LayerNorm epilogue needs ln_stats, ln_s, an even ln_slices and ln_width");
   if (a.epi == EPI_PATCH_F32 && (a.pos == nullptr || a.patches <= 0))
     return set_error(KB_ERR_ARG, "gemm: patch epilogue without pos/patches");
   // Variant choice: CTA-pair 256x256 tiles when they fill the machine; otherwise 128-row tiles, 256 wide when

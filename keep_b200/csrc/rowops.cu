@@ -104,6 +104,42 @@ __global__ void cast_kernel(const float* __restrict__ src, uint16_t* __restrict_
   }
 }
 
+// One warp per output row n of W[N,K]: W'[n,:] = 16-bit(W[n,:] * lnw), s[n] = sum of the rounded W'[n,:],
+// c[n] = bias[n] + <lnb, W[n,:]>  (LayerNorm folded into the following Linear; see EPI_LN_* in common.h)
+__global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ W, int N, int K,
+                                                      const float* __restrict__ lnw, const float* __restrict__ lnb,
+                                                      const float* __restrict__ bias, uint16_t* __restrict__ W16,
+                                                      int bf16, float* __restrict__ s, float* __restrict__ c) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  const float4* wr = reinterpret_cast<const float4*>(W + (long long)n * K);
+  float ssum = 0.f, csum = 0.f;
+  for (int k4 = lane; k4 < K / 4; k4 += 32) {
+    const float4 w = wr[k4];
+    const float4 g = __ldg(reinterpret_cast<const float4*>(lnw) + k4), b = __ldg(reinterpret_cast<const float4*>(lnb) + k4);
+    const float4 f = make_float4(w.x * g.x, w.y * g.y, w.z * g.z, w.w * g.w);
+    const uint2 pk = pack4(f, bf16);
+    *reinterpret_cast<uint2*>(W16 + (long long)n * K + k4 * 4) = pk;
+    float r0, r1, r2, r3;
+    if (bf16) {
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&pk.x), d = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
+      r0 = __low2float(a); r1 = __high2float(a); r2 = __low2float(d); r3 = __high2float(d);
+    } else {
+      const __half2 a = *reinterpret_cast<const __half2*>(&pk.x), d = *reinterpret_cast<const __half2*>(&pk.y);
+      r0 = __low2float(a); r1 = __high2float(a); r2 = __low2float(d); r3 = __high2float(d);
+    }
+    ssum += (r0 + r1) + (r2 + r3);
+    csum += (w.x * b.x + w.y * b.y) + (w.z * b.z + w.w * b.w);
+  }
+  ssum = warp_sum(ssum);
+  csum = warp_sum(csum);
+  if (lane == 0) {
+    s[n] = ssum;
+    c[n] = csum + (bias != nullptr ? bias[n] : 0.f);
+  }
+}
+
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
   __shared__ float t[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -163,6 +199,15 @@ int launch_cast_f32_to_16(const float* src, void* dst, int64_t n, int bf16, cuda
   unsigned grid = (unsigned)((n4 + 255) / 256);
   if (grid > (unsigned)num_sms() * 16) grid = num_sms() * 16;
   cast_kernel<<<grid, 256, 0, stream>>>(src, (uint16_t*)dst, n4, bf16);
+  note_launch();
+  KB_CUDA_CHECK(cudaGetLastError());
+  return KB_OK;
+}
+
+int launch_fold_ln(const float* W, int N, int K, const float* lnw, const float* lnb, const float* bias, void* W16,
+                   int bf16, float* s, float* c, cudaStream_t stream) {
+  if (N <= 0 || K <= 0 || K % 4 != 0) return set_error(KB_ERR_ARG, "fold_ln: bad shape %dx%d", N, K);
+  fold_ln_kernel<<<(N + 7) / 8, 256, 0, stream>>>(W, N, K, lnw, lnb, bias, (uint16_t*)W16, bf16, s, c);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;

@@ -52,6 +52,54 @@ def gemm(a, w, epi, bias=None, gamma=None, resid=None, out=None, pos=None, patch
     return out
 
 
+def gemm_resid_stats(a, w, x, bias=None, gamma=None):
+    """x[M,N] += gamma * (a @ w.T + bias) in place; returns (x16, stats[M, N/64, 2]) of the new x."""
+    _need_cuda(a, w, x, bias, gamma)
+    M, K = a.shape
+    N = w.shape[0]
+    assert x.shape == (M, N) and x.dtype == torch.float32 and x.is_contiguous() and a.is_contiguous() and w.is_contiguous()
+    x16 = torch.empty(M, N, dtype=a.dtype, device=a.device)
+    stats = torch.zeros(M, N // 64, 2, dtype=torch.float32, device=a.device)
+    L = _lib.lib()
+    _lib.check(
+        L.keepb200_op_gemm_resid_stats(a.data_ptr(), w.data_ptr(), M, N, K, _is_bf16(a), _lib.ptr(bias), _lib.ptr(gamma),
+                                       x.data_ptr(), x16.data_ptr(), stats.data_ptr(), _lib.stream_ptr(a.device)),
+        "op_gemm_resid_stats",
+    )
+    return x16, stats
+
+
+def fold_ln(w32, lnw, lnb, bias, dtype=torch.float16):
+    """LayerNorm folded into the following Linear: returns (W16, s, c)."""
+    _need_cuda(w32, lnw, lnb, bias)
+    N, K = w32.shape
+    w16 = torch.empty(N, K, dtype=dtype, device=w32.device)
+    s = torch.empty(N, dtype=torch.float32, device=w32.device)
+    c = torch.empty(N, dtype=torch.float32, device=w32.device)
+    L = _lib.lib()
+    _lib.check(
+        L.keepb200_op_fold_ln(w32.data_ptr(), N, K, lnw.data_ptr(), lnb.data_ptr(), _lib.ptr(bias), w16.data_ptr(),
+                              1 if dtype == torch.bfloat16 else 0, s.data_ptr(), c.data_ptr(), _lib.stream_ptr(w32.device)),
+        "op_fold_ln",
+    )
+    return w16, s, c
+
+
+def gemm_ln(x16, wf, s, c, stats, eps, gelu=False):
+    """act(Linear(LayerNorm(x))) from the 16-bit copy of x, its row statistics and the folded weight."""
+    _need_cuda(x16, wf, s, c, stats)
+    M, K = x16.shape
+    N = wf.shape[0]
+    out = torch.empty(M, N, dtype=x16.dtype, device=x16.device)
+    L = _lib.lib()
+    _lib.check(
+        L.keepb200_op_gemm_ln(x16.data_ptr(), wf.data_ptr(), M, N, K, 1 if gelu else 0, _is_bf16(x16), c.data_ptr(),
+                              s.data_ptr(), stats.data_ptr(), eps, out.data_ptr(), _lib.stream_ptr(x16.device)),
+        "op_gemm_ln",
+    )
+    return out
+
+
 def layernorm(x, w, b, eps, out_dtype=torch.float16, want_f32=False, rows=None, row_stride=None):
     _need_cuda(x, w, b)
     D = w.numel()

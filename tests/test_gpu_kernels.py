@@ -251,3 +251,64 @@ def test_refine_bit_exact_vs_dict_walk(overlap, C):
     got = refined.cpu().numpy()
     for (x, y), i in first.items():
         assert np.array_equal(got[i], exp[(x, y)]), (x, y)
+
+
+# ---- LayerNorm fused across two GEMMs (EPI_RESID_F32_STATS -> EPI_LN_*) ------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(197 * 3, 1024, 1024), (197 * 40 + 5, 1024, 4096), (77, 256, 128)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_gemm_resid_stats_matches_residual_and_row_sums(M, N, K, dtype):
+    """The stats-producing residual epilogue: same x as EPI_RESID_F32, x16 = 16-bit(x), and per-row partial sums
+    over 64-column slices that add up to the row sum / sum of squares of the NEW x."""
+    from keep_b200 import ops
+
+    a, w, bias, gamma, g = _gemm_inputs(M, N, K, dtype)
+    resid = torch.randn(M, N, generator=g).to(DEV)
+    plain = ops.gemm(a, w, ops.EPI_RESID_F32, bias=bias, gamma=gamma, resid=resid.clone())
+    x = resid.clone()
+    x16, stats = ops.gemm_resid_stats(a, w, x, bias=bias, gamma=gamma)
+    assert torch.equal(x, plain)                       # bit-identical fp32 residual update
+    assert torch.equal(x16, x.to(dtype))               # round-to-nearest copy
+    xs = x.view(M, N // 64, 64)
+    assert torch.allclose(stats[..., 0], xs.sum(-1), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(stats[..., 1], (xs * xs).sum(-1), rtol=1e-5, atol=1e-4)
+    # deterministic: fixed reduction order, no atomics
+    x2 = resid.clone()
+    _, stats2 = ops.gemm_resid_stats(a, w, x2, bias=bias, gamma=gamma)
+    assert torch.equal(stats, stats2)
+
+
+@pytest.mark.parametrize("M,N,K,gelu", [(197 * 3, 3072, 1024, False), (197 * 40 + 5, 4096, 1024, True),
+                                         (197 * 70, 3072, 1024, False), (61, 256, 128, True)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_gemm_ln_equals_layernorm_then_linear(M, N, K, gelu, dtype):
+    """fold_ln + EPI_LN_*: act(Linear(LayerNorm(x))) computed from 16-bit(x), the row statistics of x and the
+    folded weight, against the fp32 statement; also against the two-kernel product path (layernorm -> gemm), whose
+    error it must not exceed by more than rounding noise."""
+    from keep_b200 import ops
+
+    g = torch.Generator().manual_seed(M + N + K)
+    x = (torch.randn(M, K, generator=g) * 1.7 + 0.05 * torch.randn(M, 1, generator=g)).to(DEV)
+    x[:, 3] += 6.0                                         # one heavy channel, as ViT residual streams have
+    w32 = (torch.randn(N, K, generator=g) * 0.03).to(DEV)
+    bias = (torch.randn(N, generator=g) * 0.1).to(DEV)
+    lnw = (1 + 0.1 * torch.randn(K, generator=g)).to(DEV)
+    lnb = (0.05 * torch.randn(K, generator=g)).to(DEV)
+    eps = 1e-6
+    ref = F.layer_norm(x.double(), (K,), lnw.double(), lnb.double(), eps) @ w32.double().T + bias.double()
+    if gelu:
+        ref = F.gelu(ref)
+    # statistics as the producer leaves them: per 64-column slice
+    xs = x.view(M, K // 64, 64)
+    stats = torch.stack([xs.sum(-1), (xs * xs).sum(-1)], dim=-1).contiguous()
+    wf, s, c = ops.fold_ln(w32, lnw, lnb, bias, dtype=dtype)
+    assert torch.equal(wf, (w32 * lnw).to(dtype))
+    assert torch.allclose(s, wf.float().sum(1), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(c, (bias.double() + w32.double() @ lnb.double()).float(), rtol=1e-5, atol=1e-5)
+    out = ops.gemm_ln(x.to(dtype), wf, s, c, stats, eps, gelu=gelu)
+    xn = ops.layernorm(x, lnw, lnb, eps, out_dtype=dtype)[0]
+    two = ops.gemm(xn, w32.to(dtype), ops.EPI_BIAS_GELU_HALF if gelu else ops.EPI_BIAS_HALF, bias=bias)
+    e_fused = ((out.double() - ref).norm() / ref.norm()).item()
+    e_two = ((two.double() - ref).norm() / ref.norm()).item()
+    tol = 1.5e-3 if dtype == torch.float16 else 1.2e-2
+    assert e_fused < tol, (e_fused, e_two)
+    assert e_fused < 1.5 * e_two + 1e-4, (e_fused, e_two)

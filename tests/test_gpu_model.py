@@ -91,6 +91,34 @@ def test_full_model_batch_vs_oracle(full_pair):
     assert rl_t <= FP16_REL and cos_t >= FP16_COS, (rl_t, cos_t)
 
 
+def test_fused_layernorm_paths_match_standalone_layernorm(full_pair):
+    """The image path folds norm1 (KEEPB200_LN_FUSE=1, default) or norm1 and norm2 (=2) into the following GEMMs
+    (EPI_LN_*); =0 runs the stand-alone LayerNorm kernel in every block. All three must sit inside the parity gate
+    and agree with each other."""
+    import os
+
+    oracle, prod, _ = full_pair
+    g = torch.Generator().manual_seed(7)
+    tiles = torch.randn(5, 3, 224, 224, generator=g)
+    with torch.no_grad():
+        ref = oracle.encode_image(tiles)
+    outs = {}
+    try:
+        for mode in ("0", "1", "2"):
+            os.environ["KEEPB200_LN_FUSE"] = mode
+            outs[mode] = prod.encode_image(tiles.to(DEV)).clone()
+    finally:
+        del os.environ["KEEPB200_LN_FUSE"]
+    for mode, out in outs.items():
+        rl, cos = common.row_metrics(out, ref)
+        rl0, _ = common.row_metrics(out, outs["0"])
+        print(f"KEEPB200_LN_FUSE={mode}: rel-L2 vs fp32 oracle {rl:.2e} (cos {cos:.7f}); vs stand-alone LN {rl0:.2e}")
+        assert rl <= FP16_REL and cos >= FP16_COS, (mode, rl, cos)
+        assert rl0 <= FP16_REL
+    assert not torch.equal(outs["0"], outs["1"]) and not torch.equal(outs["1"], outs["2"])  # the toggle switches paths
+    assert torch.equal(outs["1"], prod.encode_image(tiles.to(DEV)))  # default = mode 1, and deterministic
+
+
 def test_batch_invariance_and_chunking(tiny_pair):
     """Same tile alone, inside a batch, and across workspace chunks gives the same embedding."""
     _, prod, _, _ = tiny_pair
