@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -s 2>&1 | grep -v "^$" | tail -12
-for v in 0 1 2 0 1 2; do
-KEEPB200_LN_FUSE=$v timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_fuse$v.json 2> gpurun_out/bench_tmp.err; python -c "
-import json;d=json.load(open('gpurun_out/bench_fuse$v.json'));print('fuse=$v', d['value'], d['roofline']['achieved'], d['clocks']['sm_mhz'], [(r['N'],r['K'],r['epi'],r['tflops']) for r in d['roofline']['per_shape'][:5]])"
-done
+N=${1:-2}
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+echo "exit $?"; cat gpurun_out/bench_n$N.json; tail -5 gpurun_out/bench_n$N.err
