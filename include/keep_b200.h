@@ -111,6 +111,12 @@ size_t keepb200_workspace_bytes(void* handle, int op, int64_t n, int64_t seq_len
  * The batch is processed in chunks as large as the workspace allows (>= 1 tile). */
 int keepb200_encode_image(void* handle, const void* tiles, int layout, int64_t B, float* out, void* workspace,
                           size_t workspace_bytes, void* stream);
+/* Tiles of another size, H and W multiples of 16 with (H/16)*(W/16) + 1 <= 512 tokens: the reference builds its ViT with
+ * dynamic_img_size=True (keep_inference.py:39), i.e. timm resamples pos_embed to the new patch grid (bicubic, antialias,
+ * prefix token kept). keepb200_encode_image == this call with H = W = img_size. */
+size_t keepb200_workspace_bytes_hw(void* handle, int64_t n, int64_t H, int64_t W);
+int keepb200_encode_image_hw(void* handle, const void* tiles, int layout, int64_t B, int64_t H, int64_t W, float* out,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* out[P, hidden] fp32, unit L2 norm = normalize(BertModel(ids, type_ids, mask).pooler_output)
  * (keep_inference.py:60-62). ids/type_ids/mask are int64 [P,S] row-major (type_ids or mask may be NULL:
@@ -176,6 +182,8 @@ int keepb200_op_gemm_ln(const void* x16, const void* Wf, int M, int N, int K, in
                         const float* s_vec, const float* stats, float eps, void* out16, void* stream);
 int keepb200_op_fold_ln(const float* W, int N, int K, const float* lnw, const float* lnb, const float* bias, void* W16,
                         int bf16, float* s, float* c, void* stream);
+/* pos_embed [1 + G0*G0, D] -> out [1 + Gh*Gw, D] (timm resample_abs_pos_embed: bicubic, antialias=True, 1 prefix token) */
+int keepb200_op_pos_resample(const float* pos, int G0, int Gh, int Gw, int D, float* out, void* stream);
 int keepb200_op_layernorm(const float* x, int64_t row_stride, int64_t rows, int D, const float* w, const float* b,
                           float eps, void* y16, int bf16, float* y32, void* stream);
 int keepb200_op_attention(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,

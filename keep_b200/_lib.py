@@ -59,6 +59,8 @@ SIGNATURES = {
     "keepb200_finalize": (_int, [_p]),
     "keepb200_workspace_bytes": (_sz, [_p, _int, _i64, _i64]),
     "keepb200_encode_image": (_int, [_p, _p, _int, _i64, _p, _p, _sz, _p]),
+    "keepb200_workspace_bytes_hw": (_sz, [_p, _i64, _i64, _i64]),
+    "keepb200_encode_image_hw": (_int, [_p, _p, _int, _i64, _i64, _i64, _p, _p, _sz, _p]),
     "keepb200_encode_text": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _sz, _p]),
     "keepb200_similarity": (_int, [_p, _i64, _i64, _p, _i64, _int, _f, _p, _p, _p, _sz, _p]),
     "keepb200_similarity_workspace_bytes": (_sz, [_i64, _i64]),
@@ -74,6 +76,7 @@ SIGNATURES = {
     "keepb200_op_gemm_resid_stats": (_int, [_p, _p, _int, _int, _int, _int, _p, _p, _p, _p, _p, _p]),
     "keepb200_op_gemm_ln": (_int, [_p, _p, _int, _int, _int, _int, _int, _p, _p, _p, _f, _p, _p]),
     "keepb200_op_fold_ln": (_int, [_p, _int, _int, _p, _p, _p, _p, _int, _p, _p, _p]),
+    "keepb200_op_pos_resample": (_int, [_p, _int, _int, _int, _int, _p, _p]),
     "keepb200_op_layernorm": (_int, [_p, _i64, _i64, _int, _p, _p, _f, _p, _int, _p, _p]),
     "keepb200_op_attention": (_int, [_p, _p, _int, _int, _int, _int, _p, _i64, _f, _p]),
     "keepb200_debug_attention_trace": (_int, [_p]),

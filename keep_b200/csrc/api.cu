@@ -235,13 +235,15 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- workspace layouts -------------------------------------------------------------------------------------
 struct ImageWs {
-  size_t x, xn, qkv, att, hid, xc, cls16, h1, feat, stats, total;
+  size_t x, xn, qkv, att, hid, xc, cls16, h1, feat, stats, pos, total;
 };
-ImageWs image_ws(const Model* m, int64_t n) {
+// gh x gw = patch grid of the tiles (the model's own grid unless dynamic_img_size is exercised)
+ImageWs image_ws(const Model* m, int64_t n, int gh, int gw) {
   const KeepB200Config& c = m->cfg;
-  const size_t M = (size_t)n * m->tokens();
+  const size_t T = (size_t)gh * gw + 1;
+  const size_t M = (size_t)n * T;
   const size_t D = c.vit_width, F = c.vit_mlp;
-  const size_t patch_bytes = (size_t)n * (m->tokens() - 1) * 768 * 2;
+  const size_t patch_bytes = (size_t)n * (T - 1) * 768 * 2;
   ImageWs w;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
@@ -257,6 +259,7 @@ ImageWs image_ws(const Model* m, int64_t n) {
   w.h1 = take((size_t)n * c.proj_dim * 2);
   w.feat = take((size_t)n * c.proj_dim * 4);
   w.stats = take(M * (D / kLnSliceCols) * 8);  // LayerNorm partial sums of the residual rows (fused-LN path)
+  w.pos = take((gh == m->grid() && gw == m->grid()) ? 0 : T * D * 4);  // resampled pos_embed (dynamic_img_size)
   w.total = off;
   return w;
 }
@@ -318,11 +321,12 @@ int gemm_ln(const void* x16, int D, const void* Wf, int M, int N, int epi, int b
   return launch_gemm(a, st);
 }
 
-int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, float* out, char* ws, cudaStream_t st) {
+int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, int gh, int gw, float* out, char* ws,
+                       cudaStream_t st) {
   const KeepB200Config& c = m->cfg;
-  const int bf = c.operand_dtype, D = c.vit_width, F = c.vit_mlp, T = m->tokens(), G = m->grid();
+  const int bf = c.operand_dtype, D = c.vit_width, F = c.vit_mlp, T = gh * gw + 1;
   const int M = (int)(n * T);
-  const ImageWs w = image_ws(m, n);
+  const ImageWs w = image_ws(m, n, gh, gw);
   float* x = reinterpret_cast<float*>(ws + w.x);
   void* xn = ws + w.xn;
   void* qkv = ws + w.qkv;
@@ -338,13 +342,20 @@ int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, float
   // embedding) and the CLS-row tail of the last block use the stand-alone kernel.
   const int fuse = ln_fuse_mode();
 
+  // dynamic_img_size (keep_inference.py:39): other grids use pos_embed resampled like timm's resample_abs_pos_embed
+  const float* pos = m->pos;
+  if (gh != m->grid() || gw != m->grid()) {
+    float* rp = reinterpret_cast<float*>(ws + w.pos);
+    KB_TRY(launch_pos_resample(m->pos, m->grid(), gh, gw, D, rp, st));
+    pos = rp;
+  }
   // patch gather (+ CLS rows), then patch-embed GEMM scattering into x[b, 1+p, :] with +bias +pos
   if (layout == KEEPB200_TILES_F32_NCHW)
-    KB_TRY(launch_im2col(static_cast<const float*>(tiles), n, G, hid, bf, m->cls, m->pos, x, D, st));
+    KB_TRY(launch_im2col(static_cast<const float*>(tiles), n, gh, gw, hid, bf, m->cls, pos, x, D, st));
   else
-    KB_TRY(launch_im2col_u8(static_cast<const uint8_t*>(tiles), n, G, hid, bf, m->cls, m->pos, x, D, st));
+    KB_TRY(launch_im2col_u8(static_cast<const uint8_t*>(tiles), n, gh, gw, hid, bf, m->cls, pos, x, D, st));
   KB_TRY(gemm(hid, 768, m->pe_w, (int)(n * (T - 1)), D, 768, EPI_PATCH_F32, bf, m->pe_b, nullptr, nullptr, x, D, st,
-              m->pos, T - 1));
+              pos, T - 1));
   for (int i = 0; i < c.vit_depth; ++i) {
     const VitBlock& b = m->blocks[i];
     if (fuse >= 1 && i > 0) {
@@ -553,13 +564,34 @@ int keepb200_finalize(void* handle) {
 size_t keepb200_workspace_bytes(void* handle, int op, int64_t n, int64_t seq_len) {
   if (!handle || n <= 0) return 0;
   Model* m = static_cast<Model*>(handle);
-  if (op == KEEPB200_OP_ENCODE_IMAGE) return image_ws(m, n).total;
+  if (op == KEEPB200_OP_ENCODE_IMAGE) return image_ws(m, n, m->grid(), m->grid()).total;
   if (op == KEEPB200_OP_ENCODE_TEXT) return text_ws(m, n, seq_len > 0 ? seq_len : m->cfg.max_pos).total;
   return 0;
 }
 
-int keepb200_encode_image(void* handle, const void* tiles, int layout, int64_t B, float* out, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+static int check_hw(const Model* m, int64_t H, int64_t W, int* gh, int* gw) {
+  if (H <= 0 || W <= 0 || H % 16 != 0 || W % 16 != 0)
+    return set_error(KB_ERR_ARG, "encode_image: tile size %lldx%lld must be a positive multiple of the 16-pixel patch",
+                     (long long)H, (long long)W);
+  *gh = (int)(H / 16);
+  *gw = (int)(W / 16);
+  if ((long long)*gh * *gw + 1 > 512)
+    return set_error(KB_ERR_ARG, "encode_image: %lldx%lld gives %lld tokens; the attention kernels serve <= 512",
+                     (long long)H, (long long)W, (long long)*gh * *gw + 1);
+  (void)m;
+  return KB_OK;
+}
+
+size_t keepb200_workspace_bytes_hw(void* handle, int64_t n, int64_t H, int64_t W) {
+  if (!handle || n <= 0) return 0;
+  Model* m = static_cast<Model*>(handle);
+  int gh, gw;
+  if (check_hw(m, H, W, &gh, &gw) != KB_OK) return 0;
+  return image_ws(m, n, gh, gw).total;
+}
+
+int keepb200_encode_image_hw(void* handle, const void* tiles, int layout, int64_t B, int64_t H, int64_t W, float* out,
+                             void* workspace, size_t workspace_bytes, void* stream) {
   if (!handle) return set_error(KB_ERR_ARG, "null handle");
   Model* m = static_cast<Model*>(handle);
   if (!m->finalized) return set_error(KB_ERR_STATE, "encode_image: handle not finalised");
@@ -567,27 +599,38 @@ int keepb200_encode_image(void* handle, const void* tiles, int layout, int64_t B
   if (B < 0 || !tiles || !out) return set_error(KB_ERR_ARG, "encode_image: bad arguments");
   if (layout != KEEPB200_TILES_F32_NCHW && layout != KEEPB200_TILES_U8_NHWC)
     return set_error(KB_ERR_ARG, "encode_image: unknown tile layout %d", layout);
+  int gh, gw;
+  KB_TRY(check_hw(m, H, W, &gh, &gw));
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return set_error(KB_ERR_ARG, "encode_image: workspace must be 1024-byte aligned");
-  const size_t per1 = image_ws(m, 1).total;
+  const size_t per1 = image_ws(m, 1, gh, gw).total;
   if (!workspace || workspace_bytes < per1)
     return set_error(KB_ERR_WORKSPACE, "encode_image: workspace %zu B < %zu B needed for one tile", workspace_bytes, per1);
   // largest chunk that fits (the layout is monotone in n); rows are limited to int32 GEMM extents
+  const int64_t T = (int64_t)gh * gw + 1;
   int64_t chunk = B;
   const int64_t max_rows = (int64_t)1 << 30;
-  if (chunk * m->tokens() > max_rows) chunk = max_rows / m->tokens();
-  while (chunk > 1 && image_ws(m, chunk).total > workspace_bytes) {
-    int64_t guess = (int64_t)(workspace_bytes / (image_ws(m, chunk).total / (double)chunk));
+  if (chunk * T > max_rows) chunk = max_rows / T;
+  while (chunk > 1 && image_ws(m, chunk, gh, gw).total > workspace_bytes) {
+    int64_t guess = (int64_t)(workspace_bytes / (image_ws(m, chunk, gh, gw).total / (double)chunk));
     chunk = guess < chunk ? (guess > 1 ? guess : 1) : chunk - 1;
   }
-  const size_t tile_elems = (size_t)3 * m->cfg.img_size * m->cfg.img_size;
+  const size_t tile_elems = (size_t)3 * H * W;
   const size_t tile_bytes = tile_elems * (layout == KEEPB200_TILES_F32_NCHW ? 4 : 1);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {
     const int64_t n = (B - b0 < chunk) ? (B - b0) : chunk;
-    KB_TRY(encode_image_chunk(m, static_cast<const char*>(tiles) + (size_t)b0 * tile_bytes, layout, n,
+    KB_TRY(encode_image_chunk(m, static_cast<const char*>(tiles) + (size_t)b0 * tile_bytes, layout, n, gh, gw,
                               out + (size_t)b0 * m->cfg.proj_dim, static_cast<char*>(workspace), st));
   }
   return KB_OK;
+}
+
+int keepb200_encode_image(void* handle, const void* tiles, int layout, int64_t B, float* out, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (!handle) return set_error(KB_ERR_ARG, "null handle");
+  const Model* m = static_cast<Model*>(handle);
+  return keepb200_encode_image_hw(handle, tiles, layout, B, m->cfg.img_size, m->cfg.img_size, out, workspace,
+                                  workspace_bytes, stream);
 }
 
 int keepb200_encode_text(void* handle, const int64_t* ids, const int64_t* type_ids, const int64_t* mask, int64_t P,
@@ -712,6 +755,9 @@ int keepb200_op_gemm_ln(const void* x16, const void* Wf, int M, int N, int K, in
 int keepb200_op_fold_ln(const float* W, int N, int K, const float* lnw, const float* lnb, const float* bias, void* W16,
                         int bf16, float* s, float* c, void* stream) {
   return launch_fold_ln(W, N, K, lnw, lnb, bias, W16, bf16, s, c, static_cast<cudaStream_t>(stream));
+}
+int keepb200_op_pos_resample(const float* pos, int G0, int Gh, int Gw, int D, float* out, void* stream) {
+  return launch_pos_resample(pos, G0, Gh, Gw, D, out, static_cast<cudaStream_t>(stream));
 }
 int keepb200_op_layernorm(const float* x, int64_t row_stride, int64_t rows, int D, const float* w, const float* b,
                           float eps, void* y16, int bf16, float* y32, void* stream) {

@@ -102,13 +102,15 @@ int launch_attention_tc(const void* qkv, void* out, int B, int S, int H, int bf1
                         int64_t mask_stride, float scale, cudaStream_t stream);
 
 // ---- ViT front end ----------------------------------------------------------------------------------------
-// tiles fp32 NCHW [B,3,G*16,G*16] -> patches16 [B*G*G, 768] (col = c*256+ky*16+kx); also writes the CLS
-// rows x[b*(G*G+1), :] = cls + pos[0].
-int launch_im2col(const float* tiles, int64_t B, int G, void* patches16, int bf16, const float* cls,
+// tiles fp32 NCHW [B,3,Gh*16,Gw*16] -> patches16 [B*Gh*Gw, 768] (col = c*256+ky*16+kx); also writes the CLS
+// rows x[b*(Gh*Gw+1), :] = cls + pos[0].
+int launch_im2col(const float* tiles, int64_t B, int Gh, int Gw, void* patches16, int bf16, const float* cls,
                   const float* pos, float* x, int D, cudaStream_t stream);
 // uint8 NHWC tiles [B,H,W,3] with fused (x/255-mean)/std
-int launch_im2col_u8(const uint8_t* tiles, int64_t B, int G, void* patches16, int bf16, const float* cls,
+int launch_im2col_u8(const uint8_t* tiles, int64_t B, int Gh, int Gw, void* patches16, int bf16, const float* cls,
                      const float* pos, float* x, int D, cudaStream_t stream);
+// pos_embed [1 + G0*G0, D] -> out [1 + Gh*Gw, D]: prefix row copied, grid rows resampled (bicubic, antialias)
+int launch_pos_resample(const float* pos, int G0, int Gh, int Gw, int D, float* out, cudaStream_t stream);
 
 // ---- BERT front end ------------------------------------------------------------------------------------------
 // x32/x16[p*S+s,:] = LN(word[ids] + type[tt] + pos[s])

@@ -21,21 +21,21 @@ __device__ __forceinline__ uint32_t pk(float a, float b, int bf16) {
 }
 
 // one thread = 8 consecutive pixels of one image row of one channel
-__global__ void im2col_f32_kernel(const float* __restrict__ tiles, long long total, int G, uint16_t* __restrict__ patches,
+__global__ void im2col_f32_kernel(const float* __restrict__ tiles, long long total, int Gh, int G, uint16_t* __restrict__ patches,
                                   int bf16) {
-  const int W = G * 16, X8 = W / 8;
+  const int W = G * 16, H = Gh * 16, X8 = W / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
     const int x8 = (int)(i % X8);
     long long t = i / X8;
-    const int y = (int)(t % W); t /= W;
+    const int y = (int)(t % H); t /= H;
     const int c = (int)(t % 3);
     const long long b = t / 3;
-    const float4* src = reinterpret_cast<const float4*>(tiles + ((b * 3 + c) * W + y) * W + x8 * 8);
+    const float4* src = reinterpret_cast<const float4*>(tiles + ((b * 3 + c) * H + y) * W + x8 * 8);
     const float4 v0 = __ldcs(src), v1 = __ldcs(src + 1);
     const int x = x8 * 8, px = x >> 4, kx = x & 15, py = y >> 4, ky = y & 15;
-    const long long row = b * G * G + py * G + px;
+    const long long row = b * Gh * G + py * G + px;
     uint4 w;
     w.x = pk(v0.x, v0.y, bf16); w.y = pk(v0.z, v0.w, bf16);
     w.z = pk(v1.x, v1.y, bf16); w.w = pk(v1.z, v1.w, bf16);
@@ -44,9 +44,9 @@ __global__ void im2col_f32_kernel(const float* __restrict__ tiles, long long tot
 }
 
 // one thread = 8 consecutive pixels (24 bytes, all 3 channels) of one image row
-__global__ void im2col_u8_kernel(const uint8_t* __restrict__ tiles, long long total, int G, uint16_t* __restrict__ patches,
+__global__ void im2col_u8_kernel(const uint8_t* __restrict__ tiles, long long total, int Gh, int G, uint16_t* __restrict__ patches,
                                  int bf16) {
-  const int W = G * 16, X8 = W / 8;
+  const int W = G * 16, H = Gh * 16, X8 = W / 8;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float istd[3] = {1.f / 0.229f, 1.f / 0.224f, 1.f / 0.225f};
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,13 +54,13 @@ __global__ void im2col_u8_kernel(const uint8_t* __restrict__ tiles, long long to
   for (; i < total; i += stride) {
     const int x8 = (int)(i % X8);
     long long t = i / X8;
-    const int y = (int)(t % W);
-    const long long b = t / W;
-    const uint2* src = reinterpret_cast<const uint2*>(tiles + ((b * W + y) * W + x8 * 8) * 3);  // 24 B, 8-aligned
+    const int y = (int)(t % H);
+    const long long b = t / H;
+    const uint2* src = reinterpret_cast<const uint2*>(tiles + ((b * H + y) * W + x8 * 8) * 3);  // 24 B, 8-aligned
     uint2 raw[3] = {src[0], src[1], src[2]};
     const uint8_t* px8 = reinterpret_cast<const uint8_t*>(raw);
     const int x = x8 * 8, px = x >> 4, kx = x & 15, py = y >> 4, ky = y & 15;
-    const long long row = b * G * G + py * G + px;
+    const long long row = b * Gh * G + py * G + px;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float f[8];
@@ -72,6 +72,63 @@ __global__ void im2col_u8_kernel(const uint8_t* __restrict__ tiles, long long to
       *reinterpret_cast<uint4*>(patches + row * 768 + c * 256 + ky * 16 + kx) = w;
     }
   }
+}
+
+// dynamic_img_size (quick_start/keep_inference.py:39 -> timm resample_abs_pos_embed): the G0 x G0 grid part of
+// pos_embed is resampled to Gh x Gw with F.interpolate(mode="bicubic", antialias=True) semantics, the prefix (CLS) row is
+// copied. Same weights as ATen's anti-aliased kernels: cubic a = -0.5, support = 2 * max(scale, 1), window
+// [int(center - support + 0.5), int(center + support + 0.5)) clipped to the input, weights normalised to sum 1;
+// separable, horizontal pass inside the vertical one. One thread = one output token x 4 channels.
+__device__ __forceinline__ float cubic_aa(float x) {
+  const float a = -0.5f;
+  x = fabsf(x);
+  if (x < 1.0f) return ((a + 2.0f) * x - (a + 3.0f)) * x * x + 1.0f;
+  if (x < 2.0f) return (((x - 5.0f) * x + 8.0f) * x - 4.0f) * a;
+  return 0.0f;
+}
+__device__ __forceinline__ void aa_span(int o, int in_size, float scale, float support, int* xmin, int* xsize, float* center) {
+  *center = scale * (o + 0.5f);
+  int lo = (int)(*center - support + 0.5f);
+  if (lo < 0) lo = 0;
+  int hi = (int)(*center + support + 0.5f);
+  if (hi > in_size) hi = in_size;
+  *xmin = lo;
+  *xsize = hi - lo;
+}
+__global__ void pos_resample_kernel(const float* __restrict__ pos, int G0, int Gh, int Gw, int D, float* __restrict__ out) {
+  const int d4 = D / 4;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)(1 + Gh * Gw) * d4) return;
+  const int c = (int)(i % d4);
+  const int tok = (int)(i / d4);
+  const float4* src = reinterpret_cast<const float4*>(pos);
+  float4* dst = reinterpret_cast<float4*>(out);
+  if (tok == 0) { dst[c] = src[c]; return; }
+  const int oy = (tok - 1) / Gw, ox = (tok - 1) % Gw;
+  const float sy = (float)G0 / (float)Gh, sx = (float)G0 / (float)Gw;
+  const float sup_y = sy >= 1.0f ? 2.0f * sy : 2.0f, sup_x = sx >= 1.0f ? 2.0f * sx : 2.0f;
+  const float inv_y = sy >= 1.0f ? 1.0f / sy : 1.0f, inv_x = sx >= 1.0f ? 1.0f / sx : 1.0f;
+  int ymin, ysize, xmin, xsize;
+  float cy, cx;
+  aa_span(oy, G0, sy, sup_y, &ymin, &ysize, &cy);
+  aa_span(ox, G0, sx, sup_x, &xmin, &xsize, &cx);
+  float tot_y = 0.f, tot_x = 0.f;
+  for (int j = 0; j < ysize; ++j) tot_y += cubic_aa((j + ymin - cy + 0.5f) * inv_y);
+  for (int j = 0; j < xsize; ++j) tot_x += cubic_aa((j + xmin - cx + 0.5f) * inv_x);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int jy = 0; jy < ysize; ++jy) {
+    float wy = cubic_aa((jy + ymin - cy + 0.5f) * inv_y);
+    if (tot_y != 0.f) wy /= tot_y;
+    float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int jx = 0; jx < xsize; ++jx) {
+      float wx = cubic_aa((jx + xmin - cx + 0.5f) * inv_x);
+      if (tot_x != 0.f) wx /= tot_x;
+      const float4 v = __ldg(src + (long long)(1 + (ymin + jy) * G0 + (xmin + jx)) * d4 + c);
+      row.x = fmaf(wx, v.x, row.x); row.y = fmaf(wx, v.y, row.y); row.z = fmaf(wx, v.z, row.z); row.w = fmaf(wx, v.w, row.w);
+    }
+    acc.x = fmaf(wy, row.x, acc.x); acc.y = fmaf(wy, row.y, acc.y); acc.z = fmaf(wy, row.z, acc.z); acc.w = fmaf(wy, row.w, acc.w);
+  }
+  dst[(long long)tok * d4 + c] = acc;
 }
 
 __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x,
@@ -152,32 +209,41 @@ static int launch_cls_rows(const float* cls, const float* pos, float* x, int64_t
   return KB_OK;
 }
 
-int launch_im2col(const float* tiles, int64_t B, int G, void* patches16, int bf16, const float* cls,
+int launch_pos_resample(const float* pos, int G0, int Gh, int Gw, int D, float* out, cudaStream_t stream) {
+  if (G0 <= 0 || Gh <= 0 || Gw <= 0 || D % 4 != 0) return set_error(KB_ERR_ARG, "pos_resample: bad shape");
+  const long long n = (long long)(1 + Gh * Gw) * (D / 4);
+  pos_resample_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(pos, G0, Gh, Gw, D, out);
+  note_launch();
+  KB_CUDA_CHECK(cudaGetLastError());
+  return KB_OK;
+}
+
+int launch_im2col(const float* tiles, int64_t B, int Gh, int G, void* patches16, int bf16, const float* cls,
                   const float* pos, float* x, int D, cudaStream_t stream) {
   if (B <= 0) return KB_OK;
   const int W = G * 16;
-  const long long total = (long long)B * 3 * W * (W / 8);
+  const long long total = (long long)B * 3 * (Gh * 16) * (W / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 32;
   if (blocks > cap) blocks = cap;
-  im2col_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tiles, total, G, (uint16_t*)patches16, bf16);
+  im2col_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tiles, total, Gh, G, (uint16_t*)patches16, bf16);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
-  return launch_cls_rows(cls, pos, x, B, G * G + 1, D, stream);
+  return launch_cls_rows(cls, pos, x, B, Gh * G + 1, D, stream);
 }
 
-int launch_im2col_u8(const uint8_t* tiles, int64_t B, int G, void* patches16, int bf16, const float* cls,
+int launch_im2col_u8(const uint8_t* tiles, int64_t B, int Gh, int G, void* patches16, int bf16, const float* cls,
                      const float* pos, float* x, int D, cudaStream_t stream) {
   if (B <= 0) return KB_OK;
   const int W = G * 16;
-  const long long total = (long long)B * W * (W / 8);
+  const long long total = (long long)B * (Gh * 16) * (W / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 32;
   if (blocks > cap) blocks = cap;
-  im2col_u8_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tiles, total, G, (uint16_t*)patches16, bf16);
+  im2col_u8_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tiles, total, Gh, G, (uint16_t*)patches16, bf16);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
-  return launch_cls_rows(cls, pos, x, B, G * G + 1, D, stream);
+  return launch_cls_rows(cls, pos, x, B, Gh * G + 1, D, stream);
 }
 
 int launch_bert_embed(const int64_t* ids, const int64_t* tts, int64_t id_stride, int64_t P, int S, int D,

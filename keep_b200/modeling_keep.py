@@ -171,30 +171,34 @@ class KEEPModel(PreTrainedModel):
             raise ValueError("encode_image expects a 4-D tensor")
         if x.device != dev:
             raise _lib.KeepB200Error(f"image_inputs on {x.device} but the model is on {dev}")
-        size = self.config.vision()["img_size"]
         if x.dtype == torch.uint8:
-            if tuple(x.shape[1:]) != (size, size, 3):
-                raise ValueError(f"uint8 tiles must be [B,{size},{size},3] (NHWC), got {tuple(x.shape)}")
-            layout = TILES_U8_NHWC
+            if x.shape[3] != 3:
+                raise ValueError(f"uint8 tiles must be [B,H,W,3] (NHWC), got {tuple(x.shape)}")
+            layout, (H, W) = TILES_U8_NHWC, x.shape[1:3]
             x = x.contiguous()
         else:
-            if tuple(x.shape[1:]) != (3, size, size):
-                # the reference's dynamic_img_size resamples pos_embed for other multiples of 16
-                # (keep_inference.py:39); not implemented here and never silently approximated
-                raise NotImplementedError(f"encode_image supports [B,3,{size},{size}] tiles only, got {tuple(x.shape)}")
-            layout = TILES_F32_NCHW
+            if x.shape[1] != 3:
+                raise ValueError(f"float tiles must be [B,3,H,W] (NCHW), got {tuple(x.shape)}")
+            layout, (H, W) = TILES_F32_NCHW, x.shape[2:4]
             x = x.to(torch.float32).contiguous()
+        # the reference ViT is built with dynamic_img_size=True (keep_inference.py:39): any multiple of the patch size
+        # is accepted and pos_embed is resampled to the new grid; 224x224 is the native grid. The attention kernels
+        # serve up to 512 tokens, larger tiles are refused (never silently approximated).
+        if H % 16 or W % 16 or H <= 0 or W <= 0:
+            raise ValueError(f"tile height and width must be multiples of the 16-pixel patch, got {H}x{W}")
+        if (H // 16) * (W // 16) + 1 > 512:
+            raise NotImplementedError(f"encode_image supports tiles of up to 511 patches, got {H}x{W}")
         B = x.shape[0]
         out = torch.empty(B, self.config.projection_dim, dtype=torch.float32, device=dev)
         if B == 0:
             return out
         L = _lib.lib()
         with torch.cuda.device(dev):
-            need = L.keepb200_workspace_bytes(self._handle, OP_ENCODE_IMAGE, min(B, self.image_chunk), 0)
+            need = L.keepb200_workspace_bytes_hw(self._handle, min(B, self.image_chunk), H, W)
             ws = self._workspace(need, dev)
             _lib.check(
-                L.keepb200_encode_image(self._handle, x.data_ptr(), layout, B, out.data_ptr(), self._aligned(ws), need,
-                                        _lib.stream_ptr(dev)),
+                L.keepb200_encode_image_hw(self._handle, x.data_ptr(), layout, B, H, W, out.data_ptr(), self._aligned(ws),
+                                           need, _lib.stream_ptr(dev)),
                 "encode_image")
         return out
 

@@ -100,6 +100,18 @@ def gemm_ln(x16, wf, s, c, stats, eps, gelu=False):
     return out
 
 
+def pos_resample(pos, g0, gh, gw):
+    """pos_embed [1 + g0*g0, D] fp32 -> [1 + gh*gw, D] (timm resample_abs_pos_embed semantics)."""
+    _need_cuda(pos)
+    D = pos.shape[-1]
+    pos = pos.reshape(1 + g0 * g0, D).contiguous()
+    out = torch.empty(1 + gh * gw, D, dtype=torch.float32, device=pos.device)
+    L = _lib.lib()
+    _lib.check(L.keepb200_op_pos_resample(pos.data_ptr(), g0, gh, gw, D, out.data_ptr(), _lib.stream_ptr(pos.device)),
+               "op_pos_resample")
+    return out
+
+
 def layernorm(x, w, b, eps, out_dtype=torch.float16, want_f32=False, rows=None, row_stride=None):
     _need_cuda(x, w, b)
     D = w.numel()

@@ -312,3 +312,20 @@ def test_gemm_ln_equals_layernorm_then_linear(M, N, K, gelu, dtype):
     tol = 1.5e-3 if dtype == torch.float16 else 1.2e-2
     assert e_fused < tol, (e_fused, e_two)
     assert e_fused < 1.5 * e_two + 1e-4, (e_fused, e_two)
+
+
+@pytest.mark.parametrize("g0,gh,gw", [(14, 16, 16), (14, 10, 14), (14, 7, 22), (14, 32, 15), (4, 14, 14), (14, 14, 14)])
+def test_pos_embed_resample_matches_torch_bicubic_antialias(g0, gh, gw):
+    """timm resample_abs_pos_embed = F.interpolate(mode='bicubic', antialias=True) on the grid rows, prefix row kept."""
+    from keep_b200 import ops
+
+    g = torch.Generator().manual_seed(g0 * 100 + gh * 10 + gw)
+    D = 256
+    pos = torch.randn(1, 1 + g0 * g0, D, generator=g)
+    grid = pos[:, 1:].reshape(1, g0, g0, D).permute(0, 3, 1, 2)
+    ref = torch.cat([pos[:, :1], F.interpolate(grid, size=(gh, gw), mode="bicubic", antialias=True)
+                     .permute(0, 2, 3, 1).reshape(1, gh * gw, D)], dim=1)[0]
+    out = ops.pos_resample(pos.to(DEV), g0, gh, gw).cpu()
+    assert out.shape == ref.shape
+    assert torch.equal(out[0], pos[0, 0])
+    assert (out - ref).abs().max().item() < 2e-6, (out - ref).abs().max().item()

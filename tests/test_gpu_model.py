@@ -184,6 +184,21 @@ def test_uint8_nhwc_tiles_match_float_path(tiny_pair):
     assert (a - b).abs().max().item() < 2e-4
 
 
+@pytest.mark.parametrize("H,W", [(256, 256), (160, 160), (224, 160), (112, 352)])
+def test_dynamic_img_size_matches_oracle(full_pair, H, W):
+    """dynamic_img_size=True (keep_inference.py:39): other multiples of 16 run with pos_embed resampled (bicubic,
+    antialias) to the new grid. 257 tokens -> mma.sync attention, 101 / 141 / 155 tokens -> tcgen05 attention."""
+    oracle, prod, _ = full_pair
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    tiles = torch.randn(3, 3, H, W, generator=g)
+    with torch.no_grad():
+        ref = oracle.encode_image(tiles)
+    out = prod.encode_image(tiles.to(DEV))
+    rl, cos = common.row_metrics(out, ref)
+    print(f"{H}x{W}: rel-L2 {rl:.2e} cos {cos:.7f}")
+    assert rl <= FP16_REL and cos >= FP16_COS, (H, W, rl, cos)
+
+
 def test_bf16_operands_reported(golden_dir):
     oracle, sd, text_cfg = common.tiny_oracle(seed=1)
     prod = common.tiny_product(sd, text_cfg, operand_dtype="bfloat16")
@@ -202,7 +217,9 @@ def test_errors_are_loud(tiny_pair):
 
     _, prod, sd, text_cfg = tiny_pair
     with pytest.raises(NotImplementedError):
-        prod.encode_image(torch.zeros(1, 3, 256, 256, device=DEV))
+        prod.encode_image(torch.zeros(1, 3, 368, 368, device=DEV))  # 530 tokens > 512: refused, not approximated
+    with pytest.raises(ValueError):
+        prod.encode_image(torch.zeros(1, 3, 230, 224, device=DEV))  # not a multiple of the patch size
     with pytest.raises(KeepB200Error):
         prod.encode_image(torch.zeros(1, 3, 224, 224))  # CPU input: no silent fallback
     assert prod.encode_image(torch.zeros(0, 3, 224, 224, device=DEV)).shape == (0, 128)

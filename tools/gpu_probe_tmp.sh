@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-N=${1:-2}
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
-echo "exit $?"; cat gpurun_out/bench_n$N.json; tail -5 gpurun_out/bench_n$N.err
+timeout 900 python -m pytest tests -m gpu -x -q -s 2>&1 | grep -v "^$" | tail -25
