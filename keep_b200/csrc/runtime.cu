@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -32,6 +33,9 @@ int num_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    // KEEPB200_SMS=<k>: size the persistent grids for k SMs (experiments with kernels of two streams side by side)
+    const char* e = std::getenv("KEEPB200_SMS");
+    if (e && std::atoi(e) >= 2 && std::atoi(e) <= n) n = std::atoi(e) & ~1;
   }
   return n;
 }

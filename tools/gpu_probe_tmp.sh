@@ -1,2 +1,6 @@
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -s 2>&1 | grep -v "^$" | tail -25
+python tools/exp_two_streams.py 1 512
+KEEPB200_SMS=74 python tools/exp_two_streams.py 2 512
+KEEPB200_SMS=74 python tools/exp_two_streams.py 2 256
+KEEPB200_SMS=148 python tools/exp_two_streams.py 2 512
+KEEPB200_SMS=112 python tools/exp_two_streams.py 2 512
+python tools/exp_two_streams.py 1 512
