@@ -47,6 +47,7 @@ class KEEPModel(PreTrainedModel):
     # image tiles per pass through the tower; bounds the activation workspace (~4.4 MB per tile)
     image_chunk = int(__import__("os").environ.get("KEEPB200_IMAGE_CHUNK", "512"))
     text_chunk_tokens = 1 << 18
+    trim_text = True  # skip positions that no row attends (bit-identical result); False = always the padded length
 
     def __init__(self, config: KEEPConfig):
         super().__init__(config)
@@ -225,6 +226,7 @@ class KEEPModel(PreTrainedModel):
         s_eff = S
         if mask is not None:
             mask = mask.to(device=dev, dtype=torch.long).contiguous()
+        if mask is not None and self.trim_text:
             # positions past the last attended key in EVERY row contribute exactly zero to the [CLS] output
             used = (mask != 0).any(dim=0).nonzero()
             s_eff = int(used.max().item()) + 1 if used.numel() else 1

@@ -1,0 +1,169 @@
+"""GPU: the hot path at BASELINE.json's full sizes. The fp32 CPU oracle cannot encode 10k-200k tiles in test time, so
+these check size-independent properties of the domain: row independence / permutation equivariance,
+unit norms, probabilities summing to one per classifier, linearity of the similarity in the classifier, exactness of
+trimming, first-occurrence de-duplication, plus the oracle itself on random sub-samples and on everything that is
+integer/index work (the refine walk at 200k tiles is compared with the reference dict walk in full)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests import common
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def full_pair():
+    oracle, sd = common.full_oracle(seed=0)
+    return oracle, common.full_product(sd)
+
+
+def _unit(x):
+    return (x.norm(dim=1) - 1).abs().max().item()
+
+
+def test_config2_detection_10k_tiles_x_32_prompts(full_pair):
+    """zeroshot_detection_WSI: 10,000 tiles in batches of 1024 (the bench workload), 16 two-class classifiers."""
+    from keep_b200 import ops
+
+    oracle, prod = full_pair
+    N, P = 10_000, 32
+    g = torch.Generator(device=DEV).manual_seed(1234)
+    tiles = torch.empty(N, 3, 224, 224, device=DEV)
+    for b0 in range(0, N, 1024):
+        tiles[b0:b0 + 1024].normal_(generator=g)
+    # duplicates planted far apart: identical tiles must give identical embeddings wherever they sit in a batch/chunk
+    tiles[9_999] = tiles[0]
+    tiles[5_123] = tiles[1_024]
+    feats = torch.cat([prod.encode_image(tiles[b0:b0 + 1024]) for b0 in range(0, N, 1024)])
+    assert feats.shape == (N, 768) and torch.isfinite(feats).all()
+    assert _unit(feats) < 1e-5
+    assert torch.equal(feats[9_999], feats[0]) and torch.equal(feats[5_123], feats[1_024])
+    # the oracle on a random sample of the 10k (fp32 CPU, a few seconds)
+    idx = torch.tensor([0, 777, 1023, 1024, 4095, 9_998])
+    with torch.no_grad():
+        ref = oracle.encode_image(tiles[idx].cpu())
+    rl, cos = common.row_metrics(feats[idx], ref)
+    assert rl <= 2e-3 and cos >= 0.99999, (rl, cos)
+    # a different batch split gives the same rows (row independence of every kernel on the path)
+    again = prod.encode_image(tiles[700:1500])
+    assert (again - feats[700:1500]).abs().max().item() < 1e-5
+    # similarity + per-classifier softmax at full size
+    text = common.ko.synthetic_text_inputs(P, seq_len=256, seed=3000)
+    cls = prod.encode_text(common.to_device(text, DEV)).t().contiguous()
+    logits, probs = ops.similarity(feats, cls, group=2, temp=10.0)
+    ref_l = feats.double() @ cls.double()
+    assert (logits.double() - ref_l).abs().max().item() <= 1e-3
+    assert (probs.view(N, 16, 2).sum(-1) - 1).abs().max().item() < 1e-5
+    assert (probs.argmax(1) == torch.softmax(ref_l.view(N, 16, 2) * 10, -1).view(N, P).argmax(1)).float().mean().item() >= 0.999
+
+
+def test_config3_subtyping_50k_x_256_similarity_properties():
+    """zeroshot_subtyping_WSI: 50,000 tile embeddings x 256 prompt columns (64 four-class classifiers)."""
+    from keep_b200 import ops
+
+    N, P, G = 50_000, 256, 4
+    g = torch.Generator(device=DEV).manual_seed(1235)
+    feats = torch.randn(N, 768, device=DEV, generator=g) * 3.0  # un-normalised on purpose: the kernel normalises
+    cls = F.normalize(torch.randn(768, P, device=DEV, generator=g), dim=0)
+    logits, probs = ops.similarity(feats, cls, group=G, temp=10.0)
+    # (1) against fp64 on a sample
+    idx = torch.randint(0, N, (512,), device=DEV, generator=g)
+    ref = F.normalize(feats[idx].double(), dim=-1) @ cls.double()
+    assert (logits[idx].double() - ref).abs().max().item() <= 1e-3
+    assert (probs[idx].double() - torch.softmax(ref.view(-1, P // G, G) * 10, -1).view(-1, P)).abs().max().item() <= 5e-3
+    # (2) cosine range, probabilities of every classifier sum to one
+    assert logits.abs().max().item() <= 1 + 1e-4
+    assert (probs.view(N, P // G, G).sum(-1) - 1).abs().max().item() < 1e-5
+    # (3) scale invariance of the rows (F.normalize) and row-permutation equivariance, bit for bit
+    l2, _ = ops.similarity(feats * 0.25, cls, group=G)
+    assert (l2 - logits).abs().max().item() < 2e-4
+    perm = torch.randperm(N, device=DEV, generator=g)
+    l3, p3 = ops.similarity(feats[perm], cls, group=G)
+    assert torch.equal(l3, logits[perm]) and torch.equal(p3, probs[perm])
+    # (4) linearity in the classifier: sim(x, a + b) = sim(x, a) + sim(x, b) (TF32 operand rounding apart)
+    c2 = F.normalize(torch.randn(768, P, device=DEV, generator=g), dim=0)
+    la, _ = ops.similarity(feats[:8192], cls, group=G)
+    lb, _ = ops.similarity(feats[:8192], c2, group=G)
+    lab, _ = ops.similarity(feats[:8192], cls + c2, group=G)
+    assert (lab - (la + lb)).abs().max().item() < 1e-3
+    # (5) subtype call: argmax of the per-class tile fraction agrees with the fp64 statement on the sample
+    cls4 = cls[:, :4].contiguous()
+    _, p4 = ops.similarity(feats, cls4, group=0)
+    frac = torch.bincount(p4.argmax(1), minlength=4).float() / N
+    ref4 = torch.softmax((F.normalize(feats.double(), dim=-1) @ cls4.double()) * 10, 1)
+    assert torch.equal(frac.argmax(), (torch.bincount(ref4.argmax(1), minlength=4).float() / N).argmax())
+
+
+def test_config4_segmentation_200k_overlapping_tiles():
+    """zeroshot_segmentation_WSI: 200,000 overlapping tiles (stride 112, patch 224) x 2 prompts, streamed in batches
+    of 1024; similarity, then refine_seg over the whole slide compared with the reference's dict walk IN FULL."""
+    from keep_b200 import ops
+    from oracle import wsi_oracle as wo
+
+    N, P, ps = 200_000, 2, 224
+    g = torch.Generator(device=DEV).manual_seed(2000)
+    feats = torch.randn(N, 768, device=DEV, generator=g)
+    cls = F.normalize(torch.randn(768, P, device=DEV, generator=g), dim=0)
+    probs = torch.empty(N, P, device=DEV)
+    for b0 in range(0, N, 1024):  # streamed
+        _, pr = ops.similarity(feats[b0:b0 + 1024], cls, group=0, temp=10.0)
+        probs[b0:b0 + 1024] = pr
+    whole = ops.similarity(feats, cls, group=0, temp=10.0)[1]
+    assert torch.equal(whole, probs)  # streaming changes nothing, bit for bit
+    assert (probs.sum(1) - 1).abs().max().item() < 1e-6
+    ref = torch.softmax((F.normalize(feats.double(), dim=-1) @ cls.double()) * 10, 1)
+    assert (probs.double() - ref).abs().max().item() <= 5e-3
+    # slide grid 500 x 400 at stride 112 (= 200,000 positions), shuffled, with 1,000 duplicated coordinates
+    ys, xs = torch.meshgrid(torch.arange(400), torch.arange(500), indexing="ij")
+    coords = torch.stack([xs.reshape(-1), ys.reshape(-1)], 1) * 112
+    cg = torch.Generator().manual_seed(7)
+    coords = coords[torch.randperm(N, generator=cg)]
+    coords[torch.randint(0, N, (1000,), generator=cg)] = coords[torch.randint(0, N, (1000,), generator=cg)]
+    keep, refined = ops.refine(coords.to(DEV), probs, ps, True)
+    pn, cn = probs.cpu().numpy(), coords.numpy()
+    first = wo._first_occurrence(cn)
+    exp_keep = np.zeros(N, dtype=np.uint8)
+    exp_keep[list(first.values())] = 1
+    assert np.array_equal(keep.cpu().numpy(), exp_keep)
+    exp = wo.refine_mean(pn, cn, ps, True)
+    got = refined.cpu().numpy()
+    order = np.fromiter(first.values(), dtype=np.int64)
+    exp_rows = np.stack([exp[k] for k in first.keys()])
+    assert np.array_equal(got[order], exp_rows)  # float32 neighbour means, bit for bit
+    # idempotence of the de-duplication: refining the kept tiles again keeps all of them
+    kept = torch.from_numpy(order)
+    keep2, _ = ops.refine(coords[kept].to(DEV), probs[kept.to(DEV)], ps, True)
+    assert int(keep2.sum()) == len(order)
+
+
+def test_config5_prompt_bank_91632_prompts(full_pair):
+    """encode_text over 11,454 disease names x 8 templates at seq_len 256: the shipped (trimmed) path on the whole
+    bank, the padded computation and the fp32 oracle on sub-samples."""
+    oracle, prod = full_pair
+    P = 11_454 * 8
+    text = common.ko.synthetic_text_inputs(P, seq_len=256, seed=3000)
+    # plant duplicates: the same prompt at both ends of the bank
+    for k in text:
+        text[k][P - 1] = text[k][0]
+    dev_text = common.to_device(text, DEV)
+    out = torch.cat([prod.encode_text({k: v[p0:p0 + 16384] for k, v in dev_text.items()}) for p0 in range(0, P, 16384)])
+    assert out.shape == (P, 768) and torch.isfinite(out).all()
+    assert _unit(out) < 1e-5
+    assert torch.equal(out[P - 1], out[0])
+    idx = torch.tensor([0, 1, 4097, 50_000, P - 2])
+    with torch.no_grad():
+        ref = oracle.encode_text({k: v[idx] for k, v in text.items()})
+    rl, cos = common.row_metrics(out[idx], ref)
+    assert rl <= 2e-3 and cos >= 0.99999, (rl, cos)
+    # trimming to the longest attended position is exact: the padded S=256 computation gives the same bits
+    sub = {k: v[20_000:20_512] for k, v in dev_text.items()}
+    old = prod.trim_text
+    try:
+        prod.trim_text = False
+        padded = prod.encode_text(sub)
+    finally:
+        prod.trim_text = old
+    assert torch.equal(padded, out[20_000:20_512])

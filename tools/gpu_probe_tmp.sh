@@ -1,6 +1,1 @@
-python tools/exp_two_streams.py 1 512
-KEEPB200_SMS=74 python tools/exp_two_streams.py 2 512
-KEEPB200_SMS=74 python tools/exp_two_streams.py 2 256
-KEEPB200_SMS=148 python tools/exp_two_streams.py 2 512
-KEEPB200_SMS=112 python tools/exp_two_streams.py 2 512
-python tools/exp_two_streams.py 1 512
+timeout 900 python -m pytest tests/test_gpu_baseline_sizes.py -m gpu -x -q -s --durations=5 2>&1 | grep -v "^$" | tail -30
