@@ -118,6 +118,15 @@ size_t keepb200_workspace_bytes_hw(void* handle, int64_t n, int64_t H, int64_t W
 int keepb200_encode_image_hw(void* handle, const void* tiles, int layout, int64_t B, int64_t H, int64_t W, float* out,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* The reference's input transform for raw RGB tiles of any size (keep_inference.py:88-90; WSI scripts :38-41):
+ * Resize(size, BICUBIC) on the PIL image (short side -> size, aspect kept) then CenterCrop(size). tiles: uint8 [B,H,W,3],
+ * out: uint8 [B,size,size,3], both device memory; the result is bit-identical to torchvision + Pillow (two-pass 8-bit
+ * resampler with 22-bit fixed-point weights). ToTensor + Normalize follow inside keepb200_encode_image(…U8_NHWC).
+ * Workspace (256-byte aligned) is only needed when a resize actually happens. */
+size_t keepb200_preprocess_workspace_bytes(int64_t B, int64_t H, int64_t W, int size);
+int keepb200_preprocess_u8(const uint8_t* tiles, int64_t B, int64_t H, int64_t W, int size, uint8_t* out, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* out[P, hidden] fp32, unit L2 norm = normalize(BertModel(ids, type_ids, mask).pooler_output)
  * (keep_inference.py:60-62). ids/type_ids/mask are int64 [P,S] row-major (type_ids or mask may be NULL:
  * zeros / ones). `s_eff` (1..S) is the number of leading positions to compute: positions >= s_eff must be

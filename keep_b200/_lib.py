@@ -61,6 +61,8 @@ SIGNATURES = {
     "keepb200_encode_image": (_int, [_p, _p, _int, _i64, _p, _p, _sz, _p]),
     "keepb200_workspace_bytes_hw": (_sz, [_p, _i64, _i64, _i64]),
     "keepb200_encode_image_hw": (_int, [_p, _p, _int, _i64, _i64, _i64, _p, _p, _sz, _p]),
+    "keepb200_preprocess_workspace_bytes": (_sz, [_i64, _i64, _i64, _int]),
+    "keepb200_preprocess_u8": (_int, [_p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
     "keepb200_encode_text": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _sz, _p]),
     "keepb200_similarity": (_int, [_p, _i64, _i64, _p, _i64, _int, _f, _p, _p, _p, _sz, _p]),
     "keepb200_similarity_workspace_bytes": (_sz, [_i64, _i64]),

@@ -664,6 +664,14 @@ int keepb200_encode_text(void* handle, const int64_t* ids, const int64_t* type_i
   return KB_OK;
 }
 
+size_t keepb200_preprocess_workspace_bytes(int64_t B, int64_t H, int64_t W, int size) {
+  return preprocess_workspace_bytes(B, H, W, size);
+}
+int keepb200_preprocess_u8(const uint8_t* tiles, int64_t B, int64_t H, int64_t W, int size, uint8_t* out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  return launch_preprocess_u8(tiles, B, H, W, size, out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 size_t keepb200_similarity_workspace_bytes(int64_t D, int64_t P) { return (D > 0 && P > 0) ? (size_t)D * P * 4 : 0; }
 
 int keepb200_similarity(const float* feats, int64_t N, int64_t D, const float* cls, int64_t P, int group, float temp,

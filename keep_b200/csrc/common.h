@@ -112,6 +112,12 @@ int launch_im2col_u8(const uint8_t* tiles, int64_t B, int Gh, int Gw, void* patc
 // pos_embed [1 + G0*G0, D] -> out [1 + Gh*Gw, D]: prefix row copied, grid rows resampled (bicubic, antialias)
 int launch_pos_resample(const float* pos, int G0, int Gh, int Gw, int D, float* out, cudaStream_t stream);
 
+// Resize(size, BICUBIC) + CenterCrop(size) of uint8 RGB tiles [B,H,W,3] -> [B,size,size,3], bit-identical to the
+// torchvision-on-PIL transform of the reference (keep_inference.py:88-90); preprocess.cu
+size_t preprocess_workspace_bytes(int64_t B, int64_t H, int64_t W, int size);
+int launch_preprocess_u8(const uint8_t* tiles, int64_t B, int64_t H, int64_t W, int size, uint8_t* out, void* ws,
+                         size_t ws_bytes, cudaStream_t stream);
+
 // ---- BERT front end ------------------------------------------------------------------------------------------
 // x32/x16[p*S+s,:] = LN(word[ids] + type[tt] + pos[s])
 int launch_bert_embed(const int64_t* ids, const int64_t* tts, int64_t id_stride, int64_t P, int S, int D,

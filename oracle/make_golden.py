@@ -11,6 +11,10 @@ The reference has no golden vectors of its own, so the pins are 
       example tile `quick_start/example.tif` after the reference transform (:88-93), rounded to fp16.
   vit_torchvision.npz
       the ViT restatement against the independent `torchvision.models.vit_l_16` (weights remapped, gamma = 1).
+  transform.npz
+      the reference's input transform (keep_inference.py:88-93: torchvision Resize(224, BICUBIC) + CenterCrop(224) on the
+      PIL image, then ToTensor + Normalize) run with the real torchvision + Pillow on seeded uint8 tiles of several
+      sizes and on quick_start/example.tif (whose raw pixels are stored too: /root/reference does not travel).
   wsi.npz
       outputs of /root/reference/WSI_evaluation/{utils,detection_utils,subtyping_utils,segment_utils}.py
       (imported as they lie, with empty stub modules for the absent h5py/openslide) on seeded inputs.
@@ -273,10 +277,54 @@ def make_wsi_goldens():
           "kept tiles", len(out["det_preds"]))
 
 
+TRANSFORM_SIZES = [(256, 256), (300, 260), (224, 298), (512, 384), (231, 227), (180, 200), (224, 224), (1024, 1024)]
+
+
+def transform_inputs():
+    """Seeded uint8 RGB tiles [H,W,3], smooth + noise so that the resampler sees both regimes."""
+    rng = np.random.default_rng(4242)
+    tiles = []
+    for (H, W) in TRANSFORM_SIZES:
+        yy, xx = np.mgrid[0:H, 0:W]
+        base = 127 + 90 * np.sin(xx / 17.0)[..., None] * np.cos(yy / 11.0)[..., None] * np.asarray([1.0, 0.7, -0.8])
+        tiles.append(np.clip(base + rng.normal(0, 40, (H, W, 3)), 0, 255).astype(np.uint8))
+    return tiles
+
+
+def make_transform_goldens():
+    from PIL import Image
+    from torchvision import transforms
+
+    resize_crop = transforms.Compose([  # keep_inference.py:88-90
+        transforms.Resize(size=224, interpolation=transforms.InterpolationMode.BICUBIC),
+        transforms.CenterCrop(size=(224, 224)),
+    ])
+    full = transforms.Compose([  # keep_inference.py:88-93
+        resize_crop, transforms.ToTensor(),
+        transforms.Normalize(mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)),
+    ])
+    out = {}
+    for i, t in enumerate(transform_inputs()):
+        out[f"u8_{i}"] = np.asarray(resize_crop(Image.fromarray(t)))
+    ex = Image.open(os.path.join(REF, "quick_start", "example.tif")).convert("RGB")
+    out["example_raw"] = np.asarray(ex)
+    out["example_u8"] = np.asarray(resize_crop(ex))
+    out["example_f32"] = full(ex).numpy()
+    import PIL
+    import torchvision
+    out["versions"] = np.asarray([PIL.__version__, torchvision.__version__])
+    np.savez_compressed(os.path.join(OUT, "transform.npz"), **out)
+    print("transform:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if len(sys.argv) > 1 and sys.argv[1] == "transform":
+        make_transform_goldens()
+        sys.exit(0)
     make_wsi_goldens()
     make_model_goldens()
+    make_transform_goldens()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

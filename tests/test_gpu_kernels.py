@@ -329,3 +329,22 @@ def test_pos_embed_resample_matches_torch_bicubic_antialias(g0, gh, gw):
     assert out.shape == ref.shape
     assert torch.equal(out[0], pos[0, 0])
     assert (out - ref).abs().max().item() < 2e-6, (out - ref).abs().max().item()
+
+
+def test_preprocess_resize_center_crop_bit_exact_vs_pil(golden_dir):
+    """Resize(224, BICUBIC) + CenterCrop(224) on uint8 tiles (keep_inference.py:88-90): bit-identical to the real
+    torchvision + Pillow output (tests/golden/transform.npz), for down-/up-sampling, both orientations, crop-only and
+    identity, and for batches."""
+    from keep_b200.transform import preprocess
+    from oracle.make_golden import transform_inputs
+
+    g = np.load(f"{golden_dir}/transform.npz")
+    for i, tile in enumerate(transform_inputs()):
+        t = torch.from_numpy(tile).to(DEV)
+        out = preprocess(torch.stack([t, t.flip(0), t]))
+        assert out.shape == (3, 224, 224, 3) and out.dtype == torch.uint8
+        assert np.array_equal(out[0].cpu().numpy(), g[f"u8_{i}"]), (i, tile.shape)
+        assert torch.equal(out[0], out[2]) and not (tile.shape[0] != 224 and torch.equal(out[0], out[1]))
+    ex = torch.from_numpy(g["example_raw"]).to(DEV)
+    assert np.array_equal(preprocess(ex[None])[0].cpu().numpy(), g["example_u8"])
+    assert preprocess(torch.zeros(0, 300, 300, 3, dtype=torch.uint8, device=DEV)).shape == (0, 224, 224, 3)

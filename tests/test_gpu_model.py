@@ -231,3 +231,19 @@ def test_errors_are_loud(tiny_pair):
     m = KEEPModel(KEEPConfig(text_config=text_cfg, vision_config=ko.TINY_VISION_CONFIG, projection_dim=128))
     with pytest.raises(RuntimeError, match="Missing key"):
         m.load_state_dict(bad, strict=True)
+
+
+def test_raw_uint8_tiles_through_transform_and_tower(full_pair, golden_dir):
+    """The reference pipeline end to end on raw pixels: transform(PIL image) -> encode_image (keep_inference.py:88-101),
+    here preprocess (device, bit-exact) -> encode_image(uint8) with ToTensor+Normalize fused into the patch gather."""
+    from keep_b200.transform import preprocess
+
+    oracle, prod, _ = full_pair
+    g = common.load_golden(golden_dir, "transform.npz")
+    raw = torch.from_numpy(g["example_raw"])                       # quick_start/example.tif, 224 x 298 RGB
+    with torch.no_grad():
+        ref = oracle.encode_image(torch.from_numpy(g["example_f32"])[None])  # the reference transform's own output
+    out = prod.encode_image(preprocess(raw[None].to(DEV)))
+    rl, cos = common.row_metrics(out, ref)
+    print(f"example.tif raw pixels -> embedding: rel-L2 {rl:.2e} cos {cos:.7f}")
+    assert rl <= FP16_REL and cos >= FP16_COS

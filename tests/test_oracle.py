@@ -121,3 +121,27 @@ def test_wsi_classifier_construction_matches_reference(golden_dir):
     np.testing.assert_allclose(c2.numpy(), g["classifier_add_normal"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(c3.numpy(), g["classifier_multi_template"], rtol=0, atol=1e-6)
     assert c2.shape == (128, 3)
+
+
+# ---- input transform (keep_inference.py:88-93): the oracle against the real torchvision + Pillow pipeline ----------
+def test_transform_oracle_matches_torchvision_pil_goldens(golden_dir):
+    from oracle import transform_oracle as to
+    from oracle.make_golden import transform_inputs
+
+    g = np.load(f"{golden_dir}/transform.npz")
+    for i, tile in enumerate(transform_inputs()):
+        assert np.array_equal(to.resize_center_crop(tile), g[f"u8_{i}"]), (i, tile.shape)  # bit-exact, every size
+    assert np.array_equal(to.resize_center_crop(g["example_raw"]), g["example_u8"])
+    assert np.abs(to.to_tensor_normalize(g["example_u8"]) - g["example_f32"]).max() <= 1e-6
+
+
+def test_transform_oracle_matches_live_pil_when_available():
+    PIL = pytest.importorskip("PIL.Image")
+    tvt = pytest.importorskip("torchvision.transforms")
+    from oracle import transform_oracle as to
+
+    tf = tvt.Compose([tvt.Resize(224, interpolation=tvt.InterpolationMode.BICUBIC), tvt.CenterCrop((224, 224))])
+    rng = np.random.default_rng(9)
+    for (H, W) in [(257, 311), (640, 480), (225, 224), (150, 333)]:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        assert np.array_equal(to.resize_center_crop(img), np.asarray(tf(PIL.fromarray(img)))), (H, W)

@@ -1,4 +1,13 @@
-mkdir -p gpurun_out
-timeout 900 python tools/bench_wsi.py > gpurun_out/bench_wsi_rows.json 2> gpurun_out/bench_wsi_rows.err; tail -3 gpurun_out/bench_wsi_rows.err; python -c "
-import json;d=json.load(open('gpurun_out/bench_wsi_rows.json'))
-for r in d['rows']: print({k:(round(v,3) if isinstance(v,float) else v) for k,v in r.items() if k not in ('kernel','cpu_note')})"
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -m gpu -x -q -s -k "preprocess or raw_uint8 or uint8" 2>&1 | grep -v "^$" | tail -12
+python - <<'PY'
+import torch, time
+from keep_b200.transform import preprocess
+x = torch.randint(0, 256, (1024, 256, 256, 3), dtype=torch.uint8, device="cuda")
+for _ in range(3): preprocess(x)
+torch.cuda.synchronize(); e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): preprocess(x)
+e1.record(); torch.cuda.synchronize()
+ms=e0.elapsed_time(e1)/10
+print(f"preprocess 1024 x 256x256 -> 224x224: {ms*1e3:.0f} us = {1024/ms*1e3:.0f} tiles/s, {(1024*(256*256*3+224*224*3))/ms/1e6:.0f} GB/s algorithmic")
+PY
