@@ -293,16 +293,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       };
       ATC_TRACE(u, EV_SM_P1);
       ATC_TRACE(u, EV_SM_BATON);
+      // TMEM loads are pipelined so that no tcgen05.wait::ld directly follows the load it would expose: wait::ld covers
+      // every outstanding load, and a tcgen05.ld takes ~250 clk in this kernel (MMAs in flight; ~35 clk on an idle SM).
+      // Invariant at the top of each step: `va` valid, `vb` (the next block) in flight since one block of work.
       uint32_t va[32], vb[32];
-      if (fast_end > 0) tmem_ld_32x32(t_row, va);
-      if (fast_end > 32) tmem_ld_32x32(t_row + 32, vb);
-      for (int c = 0; c < fast_end; c += 64) {  // two loads in flight while a block is processed
-        tmem_ld_wait_dep(va);                    // (wait::ld covers both outstanding loads: vb is complete as well)
-        exp_chunk(va, c);
-        if (c + 64 < fast_end) tmem_ld_32x32(t_row + c + 64, va);
-        if (c + 32 < fast_end) {
+      if (fast_end > 0) {
+        tmem_ld_32x32(t_row, va);
+        tmem_ld_wait_dep(va);
+        if (fast_end > 32) tmem_ld_32x32(t_row + 32, vb);
+        for (int c = 0; c < fast_end; c += 64) {
+          exp_chunk(va, c);
+          if (c + 32 >= fast_end) break;
           tmem_ld_wait_dep(vb);
+          if (c + 64 < fast_end) tmem_ld_32x32(t_row + c + 64, va);
           exp_chunk(vb, c + 32);
+          if (c + 64 >= fast_end) break;
+          tmem_ld_wait_dep(va);
           if (c + 96 < fast_end) tmem_ld_32x32(t_row + c + 96, vb);
         }
       }

@@ -292,6 +292,18 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt_ab, uint32_t M, u
 }  // namespace kb
 
 // ----------------------------------------------------------------------------------------------
+// named barriers (bar.sync / bar.arrive on ids 1..15; id 0 is __syncthreads)
+// ----------------------------------------------------------------------------------------------
+namespace kb {
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+}  // namespace kb
+
+// ----------------------------------------------------------------------------------------------
 // thread-block clusters / CTA pairs
 // ----------------------------------------------------------------------------------------------
 namespace kb {

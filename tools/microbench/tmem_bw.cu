@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(512, 1) bw_kernel(int iters, int mode, long lo
       tmem_ld_32x32(base + ((it * 64 + 32) & 511), w);
       tmem_ld_wait_dep(v);
       tmem_ld_wait_dep(w);
-      acc += v[it & 31] ^ w[(it + 7) & 31];
+      acc += v[0] ^ v[31] ^ w[0] ^ w[31];
     }
   } else {
     for (int it = 0; it < iters; ++it) {
