@@ -339,7 +339,7 @@ def main():
                        "weights": "random-init ViT-L/16 + BERT-base (no checkpoint offline)",
                        "l2": f"no flush needed: each step streams {n_tiles * 602112 / 1e9:.1f} GB of tiles (>> 126 MB L2)",
                        "parallelism": f"dp{world} tile-shard, one all-gather of [N,{N_PROMPTS}] probabilities" if world > 1 else "single GPU"},
-            "roofline": {"bound": "tensor", "kernel": "kb::gemm_kernel<BN,EPI> (tcgen05/TMA GEMM, all dense layers)",
+            "roofline": {"bound": "tensor", "kernel": "kb::gemm2_kernel<EPI> / gemm_kernel<BN,EPI> (tcgen05/TMA GEMMs: all dense layers)",
                          "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                          "frac": (ach / peaks["tflops_sustained"]) if ach else None, "traffic": traffic,
                          "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
