@@ -79,6 +79,7 @@ struct GemmArgs {
   // EPI_LN_* (consumer): statistics of the A rows ([M, ln_slices] float2 over ln_width columns), folded column sums
   const float* ln_stats = nullptr; int ln_slices = 0; int ln_width = 0; float ln_eps = 0.f;
   const float* ln_s = nullptr;   // [N]  sum_k W'[n,k]   (bias carries b.W^T + bias)
+  int cluster = 2;               // set by launch_gemm: CTAs per cluster of the pair kernel (2, or 4 = W tile multicast)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 

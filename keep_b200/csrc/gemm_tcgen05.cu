@@ -530,8 +530,11 @@ struct Cfg2 {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
 };
 
-template <int EPI, int EW>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg2<EW>::THREADS, 1)
+// CL = cluster size: 2 = one CTA pair per cluster; 4 = two pairs that work on vertically adjacent 256x256 tiles (same
+// columns of W): every CTA then loads only a 64-row quarter of the W tile and TMA-multicasts it to the CTA holding the
+// same half in the other pair, so L2 -> SMEM operand traffic per CTA and k-block drops from 32 KB to 24 KB.
+template <int EPI, int EW, int CL>
+__global__ void __launch_bounds__(Cfg2<EW>::THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const KParams p) {
   using C = Cfg2<EW>;
   constexpr int BN = C::BN;
@@ -549,10 +552,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
-  const int pair = blockIdx.x >> 1;
-  const int num_pairs = gridDim.x >> 1;
-  const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  constexpr int PAIRS = CL / 2;                  // pairs per cluster
+  const uint32_t crank = cluster_ctarank();      // rank in the cluster
+  const uint32_t rank = crank & 1;               // rank in the pair: 0 = leader (issues the MMAs)
+  const uint32_t pr = crank >> 1;                // pair index inside the cluster
+  const uint32_t leader = crank & ~1u;           // cluster rank of this pair's leader
+  const int pair = blockIdx.x / CL;              // cluster index: the unit of the persistent schedule
+  const int num_pairs = gridDim.x / CL;
+  // a cluster owns PAIRS vertically adjacent 256-row tiles ("super-tile"); the pair `pr` takes the pr-th of them
+  const int m_tiles = (p.M + PAIRS * 2 * BLOCK_M - 1) / (PAIRS * 2 * BLOCK_M);
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = p.K / BLOCK_K;
@@ -564,7 +572,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], PAIRS);  // a slot is multicast-written by every pair: all their MMAs must have read it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -588,15 +596,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       int s = 0;
       uint32_t ph = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int m_blk = (tile / n_tiles) * PAIRS + (int)pr, n_blk = tile % n_tiles;
         const int m0 = m_blk * 2 * BLOCK_M + rank * BLOCK_M;
         const int n0 = n_blk * BN + rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1, 11);
-          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[s]), 0);
+          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[s]), leader);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
           tma_load_2d_cg2(&tmap_a, leader_full, smem_a + s * C::A_BYTES, kb * BLOCK_K, m0);
-          tma_load_2d_cg2(&tmap_b, leader_full, smem_b + s * C::B_BYTES, kb * BLOCK_K, n0);
+          if constexpr (CL == 2) {
+            tma_load_2d_cg2(&tmap_b, leader_full, smem_b + s * C::B_BYTES, kb * BLOCK_K, n0);
+          } else {
+            // this CTA's quarter of the W tile (rows n0 + pr*QB .. +QB) goes to the CTAs of every pair that hold the
+            // same half (pair-rank `rank`): cluster ranks rank, rank + 2, ...; tmap_b has a QB-row box
+            constexpr int QB = (BN / 2) / PAIRS;
+            constexpr uint16_t kSameHalf = PAIRS == 2 ? 0b0101 : 0b01010101;
+            tma_load_2d_cg2_mc(&tmap_b, smem_u32(&full_bar[s]) & kPeerBitMask,
+                               smem_b + s * C::B_BYTES + pr * (QB * BLOCK_K * 2), kb * BLOCK_K, n0 + (int)pr * QB,
+                               (uint16_t)(kSameHalf << rank));
+          }
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -621,10 +639,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
             umma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_cg2_mc(&empty_bar[s], 0b11);  // free the slot in both CTAs
+          umma_commit_cg2_mc(&empty_bar[s], (uint16_t)((1u << CL) - 1));  // one arrival on the slot of every CTA of the cluster
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit_cg2_mc(&tfull_bar[as], 0b11);   // accumulator halves complete in both CTAs
+        umma_commit_cg2_mc(&tfull_bar[as], (uint16_t)(0b11u << leader));  // accumulator halves complete in both CTAs of the pair
       }
     }
   } else if (warp >= kFirstEpiWarp) {
@@ -635,20 +653,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     uint8_t* stage = smem_epi + (warp - kFirstEpiWarp) * kStageTileBytes;
     int lt = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++lt) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int m_blk = (tile / n_tiles) * PAIRS + (int)pr, n_blk = tile % n_tiles;
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       {
         const int nt = tile + num_pairs;
         if (nt < num_tiles)
-          prefetch_residual<EPI>(p, lane, (nt / n_tiles) * 2 * BLOCK_M + rank * BLOCK_M + q * 32,
+          prefetch_residual<EPI>(p, lane, ((nt / n_tiles) * PAIRS + (int)pr) * 2 * BLOCK_M + rank * BLOCK_M + q * 32,
                                  (nt % n_tiles) * BN + part * PCOLS, PCOLS);
       }
       epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * 2 * BLOCK_M + rank * BLOCK_M + q * 32, n_blk * BN,
                          part * PCOLS, (part + 1) * PCOLS, stage, &tfull_bar[as], aph, 14);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[as]), 0));
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[as]), leader));
     }
   }
 
@@ -708,21 +726,53 @@ int launch_one(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, 
   return KB_OK;
 }
 
-template <int EPI, int EW>
+// CTAs per cluster of the pair kernel. 4 = the W tile is shared by two pairs through TMA multicast: +8-10 % throughput
+// per SM, but only 33 clusters of 4 are co-resident on a B200 (132 of 148 SMs: one TPC per 9-TPC GPC is left over), so
+// the whole GEMM is 1-3 % slower than with pairs (A/B in the step: 7,152 vs 7,230 tiles/s). Default 2;
+// KEEPB200_GEMM_CLUSTER=4 selects the multicast variant (read per call: tests exercise both in one process).
+int pair_cluster_size() {
+  const char* e = std::getenv("KEEPB200_GEMM_CLUSTER");
+  return (e && std::atoi(e) == 4) ? 4 : 2;
+}
+
+template <int EPI, int EW, int CL>
 int launch_pair_ew(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   using C = Cfg2<EW>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    KB_CUDA_CHECK(cudaFuncSetAttribute(gemm2_kernel<EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+  static int max_clusters = 0;  // clusters of CL CTAs (one per SM, 227 KB of shared memory each) that can be co-resident
+  if (max_clusters == 0) {
+    KB_CUDA_CHECK(cudaFuncSetAttribute(gemm2_kernel<EPI, EW, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3((unsigned)(num_sms() / CL * CL));
+    q.blockDim = dim3(C::THREADS);
+    q.dynamicSmemBytes = C::SMEM_BYTES;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    q.attrs = &at; q.numAttrs = 1;
+    int n = 0;
+    KB_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<EPI, EW, CL>, &q));
+    if (n <= 0) return set_error(KB_ERR_CUDA, "gemm: no cluster of %d CTAs fits on this device", CL);
+    max_clusters = n;
+    if (std::getenv("KEEPB200_VERBOSE")) fprintf(stderr, "keep_b200: gemm2<epi %d> clusters of %d: %d co-resident (%d SMs)\n", EPI, CL, n, n * CL);
   }
   const KParams p = make_params(a, 2 * BLOCK_M, C::BN);
-  const int tiles = ((a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((a.N + C::BN - 1) / C::BN);
-  int pairs = num_sms() / 2;
-  if (tiles < pairs) pairs = tiles;
+  constexpr int PAIRS = CL / 2;
+  const int tiles = ((a.M + PAIRS * 2 * BLOCK_M - 1) / (PAIRS * 2 * BLOCK_M)) * ((a.N + C::BN - 1) / C::BN);
+  int clusters = num_sms() / CL;
+  if (max_clusters < clusters) clusters = max_clusters;
+  if (tiles < clusters) clusters = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(CL * clusters));
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
   profile_gemm_tag(a.M, a.N, a.K, a.epi);
   profile_gemm_begin(stream);
-  gemm2_kernel<EPI, EW><<<2 * pairs, C::THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);  // cluster dims are compile-time (2,1,1)
+  KB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm2_kernel<EPI, EW, CL>, ta, tb, p));
   profile_gemm_end(stream, 2.0 * a.M * a.N * a.K);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
@@ -732,7 +782,7 @@ int launch_pair_ew(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& 
 template <int EPI>
 int launch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   // 8 epilogue warps: a 16-warp variant (102 registers/thread) was measured no faster on fc1 and slower on proj
-  return launch_pair_ew<EPI, 8>(a, ta, tb, stream);
+  return a.cluster == 4 ? launch_pair_ew<EPI, 8, 4>(a, ta, tb, stream) : launch_pair_ew<EPI, 8, 2>(a, ta, tb, stream);
 }
 
 #define KB_DISPATCH_EPI(FN, ...)                                                             \
@@ -797,9 +847,12 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   CUtensorMap ta, tb;
   int rc = get_tmap_2d(a.A, dt, a.M, a.K, a.lda, BLOCK_M, &ta);
   if (rc) return rc;
-  rc = get_tmap_2d(a.W, dt, a.N, a.K, a.ldw, mode == 2 ? 256 : 128, &tb);
+  // pair kernel: clusters of 4 (W tile multicast between two pairs) when there are enough 512-row super-tiles
+  GemmArgs a2 = a;
+  a2.cluster = (mode == 1 && pair_cluster_size() == 4 && ((a.M + 511) / 512) * (a.N / 256) >= num_sms() / 4) ? 4 : 2;
+  rc = get_tmap_2d(a.W, dt, a.N, a.K, a.ldw, mode == 2 ? 256 : (mode == 1 && a2.cluster == 4) ? 64 : 128, &tb);
   if (rc) return rc;
-  return mode == 1 ? dispatch_pair(a, ta, tb, stream) : mode == 2 ? dispatch_256(a, ta, tb, stream) : dispatch_128(a, ta, tb, stream);
+  return mode == 1 ? dispatch_pair(a2, ta, tb, stream) : mode == 2 ? dispatch_256(a, ta, tb, stream) : dispatch_128(a, ta, tb, stream);
 }
 
 }  // namespace kb

@@ -105,6 +105,20 @@ __device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* m, uint32_t b
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// 2-CTA + multicast: the box lands at the same shared-memory offset in every CTA of `cta_mask` (cluster ranks), and the
+// bytes are credited, per destination CTA, to the mbarrier at the given CTA-relative offset in the even CTA of that
+// destination's pair (the operand is this CTA's own barrier address with the pair bit cleared, as CUTLASS's
+// SM100_TMA_2SM_LOAD_MULTICAST does).
+__device__ __forceinline__ void tma_load_2d_cg2_mc(const CUtensorMap* m, uint32_t bar_addr, void* smem_dst, int32_t c0,
+                                                   int32_t c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-pair bit of a shared-window address
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;

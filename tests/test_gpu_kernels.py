@@ -348,3 +348,36 @@ def test_preprocess_resize_center_crop_bit_exact_vs_pil(golden_dir):
     ex = torch.from_numpy(g["example_raw"]).to(DEV)
     assert np.array_equal(preprocess(ex[None])[0].cpu().numpy(), g["example_u8"])
     assert preprocess(torch.zeros(0, 300, 300, 3, dtype=torch.uint8, device=DEV)).shape == (0, 224, 224, 3)
+
+
+def test_gemm_multicast_cluster_variant_matches_pair_variant():
+    """KEEPB200_GEMM_CLUSTER=4: clusters of two CTA pairs sharing the W tile through TMA multicast. Same tiles, same
+    MMA order per tile, same epilogues => bit-identical to the default pair kernel, on every fused epilogue."""
+    import os
+    from keep_b200 import ops
+
+    M, N, K = 197 * 130 + 7, 1024, 1024           # 51 super-tiles x 4 column tiles (ragged last super-tile: second pair idle)
+    a, w, bias, gamma, g = _gemm_inputs(M, N, K, torch.float16)
+    resid = torch.randn(M, N, generator=g).to(DEV)
+    w4 = (torch.randn(4096, K, generator=g) * 0.05).half().to(DEV)
+    b4 = (torch.randn(4096, generator=g) * 0.1).to(DEV)
+
+    def run():
+        out = {}
+        out["bias"] = ops.gemm(a, w, ops.EPI_BIAS_HALF, bias=bias)
+        out["gelu"] = ops.gemm(a, w4, ops.EPI_BIAS_GELU_HALF, bias=b4)
+        out["resid"] = ops.gemm(a, w, ops.EPI_RESID_F32, bias=bias, gamma=gamma, resid=resid.clone())
+        x = resid.clone()
+        out["x16"], out["stats"] = ops.gemm_resid_stats(a, w, x, bias=bias, gamma=gamma)
+        out["x"] = x
+        return out
+
+    ref = run()
+    os.environ["KEEPB200_GEMM_CLUSTER"] = "4"
+    try:
+        got = run()
+    finally:
+        del os.environ["KEEPB200_GEMM_CLUSTER"]
+    for k in ref:
+        assert torch.equal(ref[k], got[k]), k
+    assert _rel(ref["bias"], a.float() @ w.float().T + bias) < 1e-3
