@@ -247,3 +247,25 @@ def test_raw_uint8_tiles_through_transform_and_tower(full_pair, golden_dir):
     rl, cos = common.row_metrics(out, ref)
     print(f"example.tif raw pixels -> embedding: rel-L2 {rl:.2e} cos {cos:.7f}")
     assert rl <= FP16_REL and cos >= FP16_COS
+
+
+def test_extreme_shapes_match_oracle(full_pair):
+    """Edges of the accepted input space: one single-token prompt, prompts at BERT's 512-position limit (no padding at
+    all), a tile at the 512-token limit of the attention kernels (352x352 -> 485 tokens), empty batches."""
+    from oracle import keep_oracle as ko
+
+    oracle, prod, _ = full_pair
+    one = {"input_ids": torch.tensor([[2]]), "token_type_ids": torch.tensor([[0]]), "attention_mask": torch.tensor([[1]])}
+    long = ko.synthetic_text_inputs(2, seq_len=512, seed=11, min_len=512, max_len=512)
+    tile = torch.randn(1, 3, 352, 352, generator=torch.Generator().manual_seed(12))
+    with torch.no_grad():
+        ref_one, ref_long, ref_tile = oracle.encode_text(one), oracle.encode_text(long), oracle.encode_image(tile)
+    for got, ref, what in ((prod.encode_text(common.to_device(one, DEV)), ref_one, "1-token prompt"),
+                           (prod.encode_text(common.to_device(long, DEV)), ref_long, "512-token prompts"),
+                           (prod.encode_image(tile.to(DEV)), ref_tile, "352x352 tile")):
+        rl, cos = common.row_metrics(got, ref)
+        print(f"{what}: rel-L2 {rl:.2e} cos {cos:.7f}")
+        assert rl <= FP16_REL and cos >= FP16_COS, (what, rl, cos)
+    empty = {k: v[:0] for k, v in common.to_device(long, DEV).items()}
+    assert prod.encode_text(empty).shape == (0, 768)
+    assert prod.encode_image(torch.zeros(0, 3, 224, 224, device=DEV)).shape == (0, 768)
