@@ -387,16 +387,17 @@ def test_empty_and_single_element_inputs():
     """Empty slides / single tiles / single prompts through the task kernels (the reference handles them in Python)."""
     from keep_b200 import ops
 
-    cls = F.normalize(torch.randn(768, 2, device=DEV), dim=0)
+    g = torch.Generator(device=DEV).manual_seed(77)
+    cls = F.normalize(torch.randn(768, 2, device=DEV, generator=g), dim=0)
     keep, refined = ops.refine(torch.zeros(0, 2, dtype=torch.long, device=DEV), torch.zeros(0, 2, device=DEV), 224, True)
     assert keep.shape == (0,) and refined.shape == (0, 2)
-    one = torch.softmax(torch.randn(1, 2, device=DEV), 1)
+    one = torch.softmax(torch.randn(1, 2, device=DEV, generator=g), 1)
     keep, refined = ops.refine(torch.tensor([[448, 224]], device=DEV), one, 224, True)
     assert keep.tolist() == [1] and torch.equal(refined, one)  # a lone tile is its own neighbourhood
-    x = torch.randn(1, 768, device=DEV)
+    x = torch.randn(1, 768, device=DEV, generator=g)
     lg, pr = ops.similarity(x, cls[:, :1].contiguous())        # one tile x one prompt
     assert lg.shape == (1, 1) and abs(pr.item() - 1.0) < 1e-6
     assert abs(lg.item() - (F.normalize(x, dim=-1) @ cls[:, :1]).item()) < 2e-4
     s = ops.prompt_scores(x, cls, 1, 2)                          # one tile, one two-class classifier
     l2 = (F.normalize(x, dim=-1) @ cls).flatten().sort(descending=True).values
-    assert abs(s.item() - ((l2[0] - l2[1]) - (l2[0] + l2[1] - 1).abs()).item()) < 1e-4
+    assert abs(s.item() - ((l2[0] - l2[1]) - (l2[0] + l2[1] - 1).abs()).item()) < 3e-4  # TF32 logits: ~3e-5 each
