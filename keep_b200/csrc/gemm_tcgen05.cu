@@ -25,6 +25,8 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 namespace kb {
 
@@ -680,6 +682,215 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 }
 
 // ============================================================================================================
+// CTA-pair tiles on MIXED clusters: launched with a regular cluster size of 2 and a PREFERRED size of 4
+// (cudaLaunchAttributePreferredClusterDimension), so the device forms 4-CTA clusters where a GPC has room (33 on a
+// B200 = 132 SMs) and 2-CTA clusters on the SMs left over (one TPC per 9-TPC GPC). A 4-CTA cluster shares the W tile
+// between its two pairs by TMA multicast (as gemm2_kernel<.., 4>); a 2-CTA cluster is a plain pair. Because the mix is
+// only known at run time the schedule is dynamic: warp 3 of every cluster's rank-0 CTA draws 512-row "super-tiles"
+// from a global atomic counter and publishes them to all CTAs of its cluster through a small shared-memory ring
+// (st.shared::cluster + remote mbarrier arrive); a 4-CTA cluster works on both 256-row halves at once, a pair does them
+// one after the other.
+// ============================================================================================================
+constexpr int kSchedSlots = 4;
+
+template <int EPI, int EW>
+__global__ void __launch_bounds__(Cfg2<EW>::THREADS, 1)
+gemm2d_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b128,
+              const __grid_constant__ CUtensorMap tmap_b64, const KParams p, int* sched) {
+  using C = Cfg2<EW>;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
+  uint8_t* smem_epi = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + C::EPI_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* tfull_bar = bars + 2 * C::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* sfull_bar = tempty_bar + 2;               // [kSchedSlots] per CTA: the scheduler published a super-tile
+  uint64_t* sempty_bar = sfull_bar + kSchedSlots;     // [kSchedSlots] in the rank-0 CTA: every consumer has read it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty_bar + kSchedSlots);
+  volatile int* sched_tile = reinterpret_cast<volatile int*>(tmem_slot + 1);  // [kSchedSlots]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t csize = cluster_nctaid_x();     // 4 (preferred) or 2 (regular)
+  const int PAIRS = (int)csize / 2;
+  const int SUBS = 2 / PAIRS;                    // 256-row halves of a super-tile this pair does one after the other
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1;
+  const uint32_t pr = crank >> 1;
+  const uint32_t leader = crank & ~1u;
+  const int m_super = (p.M + 4 * BLOCK_M - 1) / (4 * BLOCK_M);
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_st = m_super * n_tiles;
+  const int num_kb = p.K / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(PAIRS == 2 ? &tmap_b64 : &tmap_b128);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], PAIRS);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * EW);
+    }
+    for (int i = 0; i < kSchedSlots; ++i) {
+      mbar_init(&sfull_bar[i], 1);
+      // consumers of a published super-tile: per CTA the producer thread and EW epilogue warps, per pair the MMA thread
+      mbar_init(&sempty_bar[i], csize * (1 + EW) + PAIRS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_cg2(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // consumer side of the schedule ring: returns the next super-tile (>= num_st: no more work)
+  int sslot = 0;
+  uint32_t sph = 0;
+  auto next_super_tile = [&](bool whole_warp) {
+    mbar_wait_cluster(&sfull_bar[sslot], sph, 15);
+    const int st = sched_tile[sslot];
+    if (whole_warp) __syncwarp();
+    // Hand the slot back with a RELAXED remote arrive: a release at cluster scope would first drain this warp's global
+    // stores (the epilogue's output) - nothing is published here, the scheduler only needs to know the slot was read.
+    // The target rank is computed from `st` (always 0) so that the arrive cannot issue before the read has returned.
+    if (!whole_warp || lane == 0)
+      mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&sempty_bar[sslot]), st < 0 ? 1u : 0u));
+    if (++sslot == kSchedSlots) { sslot = 0; sph ^= 1; }
+    return st;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int st = next_super_tile(false); st < num_st; st = next_super_tile(false)) {
+        const int n_blk = st % n_tiles;
+        const int n0 = n_blk * BN + rank * (BN / 2);
+        for (int sub = 0; sub < SUBS; ++sub) {
+          const int m_blk = (st / n_tiles) * 2 + (PAIRS == 2 ? (int)pr : sub);
+          const int m0 = m_blk * 2 * BLOCK_M + rank * BLOCK_M;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&empty_bar[s], ph ^ 1, 11);
+            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[s]), leader);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+            tma_load_2d_cg2(&tmap_a, leader_full, smem_a + s * C::A_BYTES, kb * BLOCK_K, m0);
+            if (PAIRS == 1) {
+              tma_load_2d_cg2(&tmap_b128, leader_full, smem_b + s * C::B_BYTES, kb * BLOCK_K, n0);
+            } else {
+              constexpr int QB = BN / 4;  // 64-row quarter of the W tile, multicast to the same half of the other pair
+              tma_load_2d_cg2_mc(&tmap_b64, smem_u32(&full_bar[s]) & kPeerBitMask,
+                                 smem_b + s * C::B_BYTES + pr * (QB * BLOCK_K * 2), kb * BLOCK_K, n0 + (int)pr * QB,
+                                 (uint16_t)(0b0101u << rank));
+            }
+            if (++s == C::STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA of each pair) =====================
+    if (rank == 0 && lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int lt = 0;
+      const uint16_t all_ctas = (uint16_t)((1u << csize) - 1);
+      for (int st = next_super_tile(false); st < num_st; st = next_super_tile(false)) {
+        for (int sub = 0; sub < SUBS; ++sub, ++lt) {
+          const int as = lt & 1;
+          const uint32_t aph = (lt >> 1) & 1;
+          mbar_wait(&tempty_bar[as], aph ^ 1, 12);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + as * BN;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[s], ph, 13);
+            tc_fence_after();
+            const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + s * C::A_BYTES));
+            const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + s * C::B_BYTES));
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_cg2_mc(&empty_bar[s], all_ctas);
+            if (++s == C::STAGES) { s = 0; ph ^= 1; }
+          }
+          umma_commit_cg2_mc(&tfull_bar[as], (uint16_t)(0b11u << leader));
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== scheduler (rank-0 CTA of the cluster) =====================
+    if (crank == 0 && lane == 0) {
+      int slot = 0;
+      uint32_t ph = 0;
+      while (true) {
+        mbar_wait_cluster(&sempty_bar[slot], ph ^ 1, 16);
+        // A pair needs two tile times per super-tile, a 4-CTA cluster one: near the end the pairs stop drawing, so that
+        // the last super-tiles go to the clusters that finish them in half the time (tail of one tile, not two).
+        int st;
+        if (csize == 2 && *reinterpret_cast<volatile int*>(&sched[0]) >= num_st - 2 * (int)(gridDim.x / 4)) st = num_st;
+        else st = atomicAdd(&sched[0], 1);
+        for (uint32_t c = 0; c < csize; ++c) st_shared_cluster_u32(mapa_shared(smem_u32((const void*)&sched_tile[slot]), c), (uint32_t)st);
+        for (uint32_t c = 0; c < csize; ++c) mbar_arrive_cluster(mapa_shared(smem_u32(&sfull_bar[slot]), c));  // release.cluster
+        if (st >= num_st) break;
+        if (++slot == kSchedSlots) { slot = 0; ph ^= 1; }
+      }
+      atomicAdd(&sched[csize == 4 ? 3 : 2], 1);  // statistics: clusters of each size seen so far (KEEPB200_VERBOSE)
+      // the last cluster to run dry re-arms the counters for the next launch on this stream
+      __threadfence();
+      const int done = atomicAdd(&sched[1], (int)csize) + (int)csize;
+      if (done == (int)gridDim.x) {
+        sched[0] = 0;
+        sched[1] = 0;
+        __threadfence();
+      }
+    }
+  } else if (warp >= kFirstEpiWarp) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    constexpr int PARTS = EW / 4, PCOLS = BN / PARTS;
+    const int part = (warp - kFirstEpiWarp) >> 2;
+    uint8_t* stage = smem_epi + (warp - kFirstEpiWarp) * kStageTileBytes;
+    int lt = 0;
+    for (int st = next_super_tile(true); st < num_st; st = next_super_tile(true)) {
+      const int n_blk = st % n_tiles;
+      for (int sub = 0; sub < SUBS; ++sub, ++lt) {
+        const int m_blk = (st / n_tiles) * 2 + (PAIRS == 2 ? (int)pr : sub);
+        const int as = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * 2 * BLOCK_M + rank * BLOCK_M + q * 32, n_blk * BN,
+                           part * PCOLS, (part + 1) * PCOLS, stage, &tfull_bar[as], aph, 14);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[as]), leader));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ============================================================================================================
 // host side
 // ============================================================================================================
 KParams make_params(const GemmArgs& a, int umma_m, int umma_n) {
@@ -732,6 +943,7 @@ int launch_one(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, 
 // KEEPB200_GEMM_CLUSTER=4 selects the multicast variant (read per call: tests exercise both in one process).
 int pair_cluster_size() {
   const char* e = std::getenv("KEEPB200_GEMM_CLUSTER");
+  if (e && !std::strcmp(e, "mixed")) return 6;  // 4-CTA clusters where they fit + pairs on the rest, dynamic schedule
   return (e && std::atoi(e) == 4) ? 4 : 2;
 }
 
@@ -779,6 +991,59 @@ int launch_pair_ew(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& 
   return KB_OK;
 }
 
+// one {next, done} counter pair per stream (device memory, zero at rest: the kernel re-arms it)
+int* sched_counters(cudaStream_t stream) {
+  static std::mutex mu;
+  static std::map<cudaStream_t, int*> bufs;
+  std::lock_guard<std::mutex> g(mu);
+  auto it = bufs.find(stream);
+  if (it != bufs.end()) return it->second;
+  int* p = nullptr;
+  if (cudaMalloc(&p, 4 * sizeof(int)) != cudaSuccess) return nullptr;  // next, done, #pair clusters, #quad clusters
+  cudaMemset(p, 0, 4 * sizeof(int));
+  bufs[stream] = p;
+  return p;
+}
+
+template <int EPI, int EW>
+int launch_pair_dynamic(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb128, const CUtensorMap& tb64,
+                        cudaStream_t stream) {
+  using C = Cfg2<EW>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    KB_CUDA_CHECK(cudaFuncSetAttribute(gemm2d_kernel<EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    KB_CUDA_CHECK(cudaFuncSetAttribute(gemm2d_kernel<EPI, EW>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr_set = true;
+  }
+  int* sched = sched_counters(stream);
+  if (sched == nullptr) return set_error(KB_ERR_CUDA, "gemm: cannot allocate the tile-scheduler counters");
+  const KParams p = make_params(a, 2 * BLOCK_M, C::BN);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(num_sms() / 4 * 4));  // every SM; a multiple of the preferred cluster size
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributePreferredClusterDimension;
+  at[1].val.preferredClusterDim.x = 4; at[1].val.preferredClusterDim.y = 1; at[1].val.preferredClusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 2;
+  profile_gemm_tag(a.M, a.N, a.K, a.epi);
+  profile_gemm_begin(stream);
+  KB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm2d_kernel<EPI, EW>, ta, tb128, tb64, p, sched));
+  profile_gemm_end(stream, 2.0 * a.M * a.N * a.K);
+  if (std::getenv("KEEPB200_VERBOSE")) {
+    int h[4] = {0, 0, 0, 0};
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, sched, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "keep_b200: gemm2d<epi %d>: clusters so far: %d of 2 CTAs, %d of 4 CTAs\n", EPI, h[2], h[3]);
+  }
+  note_launch();
+  KB_CUDA_CHECK(cudaGetLastError());
+  return KB_OK;
+}
+
 template <int EPI>
 int launch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   // 8 epilogue warps: a 16-warp variant (102 registers/thread) was measured no faster on fc1 and slower on proj
@@ -806,6 +1071,16 @@ int dispatch_128(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb
 }
 int dispatch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   KB_DISPATCH_EPI(launch_pair, )
+}
+template <int EPI>
+int launch_pair_dyn8(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+  CUtensorMap tb64;
+  int rc = get_tmap_2d(a.W, a.bf16 ? KB_BF16 : KB_F16, a.N, a.K, a.ldw, 64, &tb64);
+  if (rc) return rc;
+  return launch_pair_dynamic<EPI, 8>(a, ta, tb, tb64, stream);
+}
+int dispatch_pair_dynamic(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+  KB_DISPATCH_EPI(launch_pair_dyn8, )
 }
 
 // KEEPB200_GEMM = auto (default) | pair | wide | narrow : force one main-loop variant (A/B measurements)
@@ -849,7 +1124,13 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   // pair kernel: clusters of 4 (W tile multicast between two pairs) when there are enough 512-row super-tiles
   GemmArgs a2 = a;
-  a2.cluster = (mode == 1 && pair_cluster_size() == 4 && ((a.M + 511) / 512) * (a.N / 256) >= num_sms() / 4) ? 4 : 2;
+  const bool many = ((a.M + 511) / 512) * (a.N / 256) >= num_sms() / 4;
+  a2.cluster = (mode == 1 && pair_cluster_size() == 4 && many) ? 4 : 2;
+  if (mode == 1 && pair_cluster_size() == 6 && many) {
+    rc = get_tmap_2d(a.W, dt, a.N, a.K, a.ldw, 128, &tb);
+    if (rc) return rc;
+    return dispatch_pair_dynamic(a2, ta, tb, stream);
+  }
   rc = get_tmap_2d(a.W, dt, a.N, a.K, a.ldw, mode == 2 ? 256 : (mode == 1 && a2.cluster == 4) ? 64 : 128, &tb);
   if (rc) return rc;
   return mode == 1 ? dispatch_pair(a2, ta, tb, stream) : mode == 2 ? dispatch_256(a, ta, tb, stream) : dispatch_128(a, ta, tb, stream);

@@ -350,9 +350,11 @@ def test_preprocess_resize_center_crop_bit_exact_vs_pil(golden_dir):
     assert preprocess(torch.zeros(0, 300, 300, 3, dtype=torch.uint8, device=DEV)).shape == (0, 224, 224, 3)
 
 
-def test_gemm_multicast_cluster_variant_matches_pair_variant():
-    """KEEPB200_GEMM_CLUSTER=4: clusters of two CTA pairs sharing the W tile through TMA multicast. Same tiles, same
-    MMA order per tile, same epilogues => bit-identical to the default pair kernel, on every fused epilogue."""
+@pytest.mark.parametrize("variant", ["2", "4", "mixed"])
+def test_gemm_multicast_cluster_variant_matches_pair_variant(variant):
+    """KEEPB200_GEMM_CLUSTER=4: clusters of two CTA pairs sharing the W tile through TMA multicast; =mixed: 4-CTA clusters
+    where the device can place them plus pairs on the remaining SMs, with a dynamic super-tile scheduler; =2: plain pairs.
+    Same tiles, same MMA order per tile, same epilogues => bit-identical to each other, on every fused epilogue."""
     import os
     from keep_b200 import ops
 
@@ -372,12 +374,19 @@ def test_gemm_multicast_cluster_variant_matches_pair_variant():
         out["x"] = x
         return out
 
-    ref = run()
-    os.environ["KEEPB200_GEMM_CLUSTER"] = "4"
+    saved = os.environ.pop("KEEPB200_GEMM_CLUSTER", None)
+    os.environ["KEEPB200_GEMM_CLUSTER"] = "2"
     try:
+        ref = run()
+        os.environ["KEEPB200_GEMM_CLUSTER"] = variant
         got = run()
+        got2 = run()   # the dynamic schedule re-arms its counters: a second launch must work and agree
     finally:
         del os.environ["KEEPB200_GEMM_CLUSTER"]
+        if saved is not None:
+            os.environ["KEEPB200_GEMM_CLUSTER"] = saved
+    for k in ref:
+        assert torch.equal(got[k], got2[k]), k
     for k in ref:
         assert torch.equal(ref[k], got[k]), k
     assert _rel(ref["bias"], a.float() @ w.float().T + bias) < 1e-3
