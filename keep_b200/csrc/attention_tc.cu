@@ -281,13 +281,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         float s0 = 0.f, s1 = 0.f;
         uint32_t pk[16];
 #pragma unroll
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(neg_m, neg_m), one2 = make_float2(1.f, 1.f);
+        float2 acc2 = make_float2(0.f, 0.f);
         for (int i = 0; i < 16; ++i) {
-          const float e0 = ex2f(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, neg_m));
-          const float e1 = ex2f(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, neg_m));
-          s0 += e0;
-          s1 += e1;
-          pk[i] = pack16(e0, e1, p.bf16);
+          // packed fp32 (FFMA2): the scale-and-shift and the running sums of two keys per instruction
+          const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
+          const float2 e = make_float2(ex2f(t.x), ex2f(t.y));
+          acc2 = __ffma2_rn(e, one2, acc2);
+          pk[i] = pack16(e.x, e.y, p.bf16);
         }
+        s0 += acc2.x;
+        s1 += acc2.y;
         sum += s0 + s1;
         tmem_st_32x16(t_row + (c >> 1), pk);
       };

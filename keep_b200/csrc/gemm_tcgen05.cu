@@ -95,6 +95,30 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-ax, e, fmaxf(x, 0.0f));
 }
 
+// Two elements at once on the packed fp32 pipe (FFMA2, sm_100): same arithmetic, same rounding per element, half the
+// FMA-pipe instructions for the polynomial and the final multiply-add.
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 m = make_float2(fminf(ax.x, 6.0f), fminf(ax.y, 6.0f));
+#if KB_GELU_DEG == 6
+  float2 p = __ffma2_rn(m, make_float2(2.904253473e-05f, 2.904253473e-05f), make_float2(-7.323236443e-04f, -7.323236443e-04f));
+  p = __ffma2_rn(m, p, make_float2(7.953787372e-03f, 7.953787372e-03f));
+  p = __ffma2_rn(m, p, make_float2(-5.320511315e-02f, -5.320511315e-02f));
+  p = __ffma2_rn(m, p, make_float2(-4.589348205e-01f, -4.589348205e-01f));
+  p = __ffma2_rn(m, p, make_float2(-1.151144948e+00f, -1.151144948e+00f));
+  p = __ffma2_rn(m, p, make_float2(-9.999990962e-01f, -9.999990962e-01f));
+#else
+  float2 p = __ffma2_rn(m, make_float2(3.920550193e-03f, 3.920550193e-03f), make_float2(-4.439129536e-02f, -4.439129536e-02f));
+  p = __ffma2_rn(m, p, make_float2(-4.674139173e-01f, -4.674139173e-01f));
+  p = __ffma2_rn(m, p, make_float2(-1.147820817e+00f, -1.147820817e+00f));
+  p = __ffma2_rn(m, p, make_float2(-1.000374045e+00f, -1.000374045e+00f));
+#endif
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(p.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(p.y));
+  return __ffma2_rn(make_float2(-ax.x, -ax.y), e, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
+}
+
 __device__ __forceinline__ uint32_t pack16(float a, float b, int bf16) {
   if (bf16) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -186,12 +210,24 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(sa));
         if constexpr (T::kLn) {
           const float nm = __shfl_sync(0xffffffffu, ln_nmu, rl), rs = __shfl_sync(0xffffffffu, ln_rstd, rl);
-          a.x = fmaf(rs, fmaf(nm, g4.x, a.x), b4.x); a.y = fmaf(rs, fmaf(nm, g4.y, a.y), b4.y);
-          a.z = fmaf(rs, fmaf(nm, g4.z, a.z), b4.z); a.w = fmaf(rs, fmaf(nm, g4.w, a.w), b4.w);
+          const float2 nm2 = make_float2(nm, nm), rs2 = make_float2(rs, rs);  // packed fp32 (FFMA2): two columns per instruction
+          const float2 lo = __ffma2_rn(rs2, __ffma2_rn(nm2, make_float2(g4.x, g4.y), make_float2(a.x, a.y)), make_float2(b4.x, b4.y));
+          const float2 hi = __ffma2_rn(rs2, __ffma2_rn(nm2, make_float2(g4.z, g4.w), make_float2(a.z, a.w)), make_float2(b4.z, b4.w));
+          a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
         } else {
-          a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+          const float2 one2 = make_float2(1.f, 1.f);  // a + b as one packed FFMA2 per two columns (exact: a * 1 + b)
+          const float2 lo = __ffma2_rn(make_float2(a.x, a.y), one2, make_float2(b4.x, b4.y));
+          const float2 hi = __ffma2_rn(make_float2(a.z, a.w), one2, make_float2(b4.z, b4.w));
+          a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
         }
+#ifdef KB_GELU_SCALAR
         a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
+#else
+        {
+          const float2 lo = gelu_erf2(make_float2(a.x, a.y)), hi = gelu_erf2(make_float2(a.z, a.w));
+          a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
+        }
+#endif
         if (r >= p.M) continue;
         uint2 w;
         w.x = pack16(a.x, a.y, p.bf16);
@@ -213,8 +249,10 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
     for (int i = 0; i < 8; ++i) {
       if constexpr (T::kLn) {
         const float nm = __shfl_sync(0xffffffffu, ln_nmu, 4 * i + tr), rs = __shfl_sync(0xffffffffu, ln_rstd, 4 * i + tr);
-        a[i].x = fmaf(rs, fmaf(nm, g4.x, a[i].x), b4.x); a[i].y = fmaf(rs, fmaf(nm, g4.y, a[i].y), b4.y);
-        a[i].z = fmaf(rs, fmaf(nm, g4.z, a[i].z), b4.z); a[i].w = fmaf(rs, fmaf(nm, g4.w, a[i].w), b4.w);
+        const float2 nm2 = make_float2(nm, nm), rs2 = make_float2(rs, rs);  // packed fp32 (FFMA2): two columns per instruction
+        const float2 lo = __ffma2_rn(rs2, __ffma2_rn(nm2, make_float2(g4.x, g4.y), make_float2(a[i].x, a[i].y)), make_float2(b4.x, b4.y));
+        const float2 hi = __ffma2_rn(rs2, __ffma2_rn(nm2, make_float2(g4.z, g4.w), make_float2(a[i].z, a[i].w)), make_float2(b4.z, b4.w));
+        a[i].x = lo.x; a[i].y = lo.y; a[i].z = hi.x; a[i].w = hi.y;
       } else {
         a[i].x += b4.x; a[i].y += b4.y; a[i].z += b4.z; a[i].w += b4.w;
       }
