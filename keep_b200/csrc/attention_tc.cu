@@ -3,17 +3,19 @@
 //
 // One persistent CTA per SM; everything between the two MMAs stays on-chip (FlashAttention-4 style roles):
 //   * unit of work = 128 query rows of one (batch, head). The keys of a head fit ONE tile (S_pad <= 224), so the
-//     whole score row is available: exact two-pass softmax, no online rescaling;
+//     whole score row is in TMEM at once: one pass over S with a lazily raised power-of-two reference (below), no
+//     rescaling of O;
 //   * warp 0      : TMA producer. Q tile(s) + K go through a 2-slot ring, V through a 3-slot ring (Q/K are dead as
 //                   soon as the S MMAs of the head are done, V only after its last PV MMA), all read straight out of
 //                   the fused q|k|v projection buffer [B*S, 3*H*64] with SWIZZLE_128B boxes;
 //   * warp 1      : MMA issuer. S = Q K^T (tcgen05.mma SS, 128 x S_pad x 16, fp32 S in TMEM region u&1), and
 //                   O = P V (tcgen05.mma TS: P is read from TMEM where it overwrote S; V is the MN-major B operand);
 //                   issue order S0 S1 | PV0 S2 | PV1 S3 | ... keeps the tensor pipe busy under the softmax;
-//   * warps 4-7 / 8-11 : two softmax groups, one per S region; a thread owns one query row: tcgen05.ld S -> row max ->
-//                   exp2 -> row sum -> 16-bit P written back over S with tcgen05.st. The exp2 pass (MUFU-bound) is
-//                   serialised between the groups with a baton so that one group's MUFU work overlaps the other
-//                   group's TMEM traffic and both MMAs;
+//   * warps 4-7 / 8-11 : two softmax groups, one per S region, each working on its own unit; a thread owns one query
+//                   row: tcgen05.ld S (one block ahead of its wait) -> exp2 against the running reference (packed fp32
+//                   FFMA2 for the scale-and-shift and the row sums, MUFU for exp2) -> 16-bit P written back over S with
+//                   tcgen05.st. What bounds the kernel is the chain S(u) -> softmax(u) -> PV(u) -> S(u+2) on a region
+//                   (DESIGN.md section 4): the other group's unit fills the gaps;
 //   * warps 12-15 : output group: tcgen05.ld O (single 64-column accumulator), divide by the row sum, store rows.
 //
 // Reference semantics: timm Attention -> F.scaled_dot_product_attention and BertSelfAttention with
@@ -95,8 +97,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint64_t* p_ready = bars + 12;   // [2] softmax group -> MMA, output group
   uint64_t* o_ready = bars + 14;   // [1] MMA -> output group
   uint64_t* o_free = bars + 15;    // [1] output group -> MMA
-  uint64_t* turn = bars + 16;      // [2] exp2-pass baton between the softmax groups
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_my = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // heads of this CTA
@@ -113,7 +114,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_init(&qk_empty[i], 1);
       mbar_init(&s_ready[i], 1);
       mbar_init(&p_ready[i], 4);  // one elected lane per softmax warp
-      mbar_init(&turn[i], 4);
     }
     for (int i = 0; i < 3; ++i) {
       mbar_init(&v_full[i], 2);   // expect_tx arrive + bias-written arrive

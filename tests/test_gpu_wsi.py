@@ -116,3 +116,14 @@ def test_raw_tiles_through_task_head(golden_dir):
     assert abs(got - exp) <= 1 / 12 + 1e-9
     with pytest.raises(ValueError):
         wsi.zero_shot_detection(cls.to(DEV), tiles.to(DEV), coords)
+
+
+def test_chunked_pinned_upload_matches_source():
+    from keep_b200 import io as kio
+
+    g = torch.Generator().manual_seed(3)
+    feats = torch.randn(10_001, 768, generator=g)
+    coords = torch.randint(0, 1 << 20, (10_001, 2), generator=g)
+    assert torch.equal(kio.to_device(feats, "cuda:0", chunk_rows=1024).cpu(), feats)
+    assert torch.equal(kio.to_device(coords, "cuda:0", chunk_rows=4096).cpu(), coords)
+    assert kio.to_device(feats[:0], "cuda:0").shape == (0, 768)

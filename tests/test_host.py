@@ -91,3 +91,42 @@ def test_product_path_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_slide_feature_files_round_trip(tmp_path):
+    """keep_b200.io.load_slide: the reference's .h5 / .pt feature files (zeroshot_detection_WSI.py:29-31, utils.py:50-60)
+    plus npz/npy; dtypes and shapes are normalised, mismatches are loud."""
+    import numpy as np
+    import pytest
+    import torch
+
+    from keep_b200 import io as kio
+
+    g = np.random.default_rng(0)
+    feats = g.standard_normal((37, 768)).astype(np.float32)
+    coords = (g.integers(0, 90, (37, 2)) * 224).astype(np.int32)
+    np.savez(tmp_path / "s.npz", features=feats, coords=coords)
+    np.save(tmp_path / "s.npy", feats.astype(np.float64))
+    torch.save(torch.from_numpy(feats), tmp_path / "bare.pt")
+    torch.save({"features": torch.from_numpy(feats), "coords": torch.from_numpy(coords)}, tmp_path / "dict.pt")
+    for name, has_coords in (("s.npz", True), ("s.npy", False), ("bare.pt", False), ("dict.pt", True)):
+        f, c = kio.load_slide(str(tmp_path / name))
+        assert f.dtype == torch.float32 and tuple(f.shape) == (37, 768) and np.allclose(f.numpy(), feats)
+        assert (c is not None) == has_coords
+        if has_coords:
+            assert c.dtype == torch.int64 and np.array_equal(c.numpy(), coords)
+    np.savez(tmp_path / "bad.npz", features=feats, coords=coords[:5])
+    with pytest.raises(ValueError):
+        kio.load_slide(str(tmp_path / "bad.npz"))
+    with pytest.raises(ValueError):
+        kio.load_slide(str(tmp_path / "slide.xyz"))
+    try:
+        import h5py
+    except ImportError:
+        with pytest.raises(ImportError):
+            kio.load_slide(str(tmp_path / "s.h5"))
+    else:
+        with h5py.File(tmp_path / "s.h5", "w") as f:
+            f["features"], f["coords"] = feats, coords
+        f2, c2 = kio.load_slide(str(tmp_path / "s.h5"))
+        assert np.allclose(f2.numpy(), feats) and np.array_equal(c2.numpy(), coords)
