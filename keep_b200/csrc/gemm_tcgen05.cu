@@ -253,12 +253,16 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
         const float2 lo = __ffma2_rn(rs2, __ffma2_rn(nm2, make_float2(g4.x, g4.y), make_float2(a[i].x, a[i].y)), make_float2(b4.x, b4.y));
         const float2 hi = __ffma2_rn(rs2, __ffma2_rn(nm2, make_float2(g4.z, g4.w), make_float2(a[i].z, a[i].w)), make_float2(b4.z, b4.w));
         a[i].x = lo.x; a[i].y = lo.y; a[i].z = hi.x; a[i].w = hi.y;
+      } else if constexpr (T::kResid) {
+        // resid + gamma * (acc + bias), two columns per packed fp32 instruction (FFMA2; a * 1 + b is an exact add)
+        const float2 one2 = make_float2(1.f, 1.f);
+        const float2 lo = __ffma2_rn(make_float2(g4.x, g4.y), __ffma2_rn(make_float2(a[i].x, a[i].y), one2, make_float2(b4.x, b4.y)),
+                                     make_float2(res[i].x, res[i].y));
+        const float2 hi = __ffma2_rn(make_float2(g4.z, g4.w), __ffma2_rn(make_float2(a[i].z, a[i].w), one2, make_float2(b4.z, b4.w)),
+                                     make_float2(res[i].z, res[i].w));
+        a[i].x = lo.x; a[i].y = lo.y; a[i].z = hi.x; a[i].w = hi.y;
       } else {
         a[i].x += b4.x; a[i].y += b4.y; a[i].z += b4.z; a[i].w += b4.w;
-      }
-      if constexpr (T::kResid) {
-        a[i].x = fmaf(g4.x, a[i].x, res[i].x); a[i].y = fmaf(g4.y, a[i].y, res[i].y);
-        a[i].z = fmaf(g4.z, a[i].z, res[i].z); a[i].w = fmaf(g4.w, a[i].w, res[i].w);
       }
       if constexpr (T::kStats) {
         st_s[i] += (a[i].x + a[i].y) + (a[i].z + a[i].w);
