@@ -226,10 +226,18 @@ class KEEPModel(PreTrainedModel):
         s_eff = S
         if mask is not None:
             mask = mask.to(device=dev, dtype=torch.long).contiguous()
-        if mask is not None and self.trim_text:
-            # positions past the last attended key in EVERY row contribute exactly zero to the [CLS] output
-            used = (mask != 0).any(dim=0).nonzero()
-            s_eff = int(used.max().item()) + 1 if used.numel() else 1
+        if mask is not None:
+            # One device->host read for both facts. A row that attends to nothing is refused: BertModel would add
+            # finfo.min to every score of that row and average V over all positions, pads included - no tokenizer
+            # produces such a row, and silently returning something else is not an option here.
+            attended = mask != 0
+            facts = torch.stack([attended.any(dim=1).all().to(torch.long),
+                                 (attended.any(dim=0).to(torch.long) * torch.arange(1, S + 1, device=dev)).max()]).tolist()
+            if not facts[0]:
+                raise ValueError("encode_text: an attention_mask row has no attended position")
+            if self.trim_text:
+                # positions past the last attended key in EVERY row contribute exactly zero to the [CLS] output
+                s_eff = max(int(facts[1]), 1)
         L = _lib.lib()
         with torch.cuda.device(dev):
             chunk = max(1, min(P, self.text_chunk_tokens // s_eff))

@@ -223,6 +223,9 @@ def test_errors_are_loud(tiny_pair):
     with pytest.raises(KeepB200Error):
         prod.encode_image(torch.zeros(1, 3, 224, 224))  # CPU input: no silent fallback
     assert prod.encode_image(torch.zeros(0, 3, 224, 224, device=DEV)).shape == (0, 128)
+    ids = torch.full((2, 8), 5, dtype=torch.long, device=DEV)
+    with pytest.raises(ValueError, match="no attended position"):
+        prod.encode_text({"input_ids": ids, "attention_mask": torch.tensor([[1, 1, 0, 0, 0, 0, 0, 0], [0] * 8], device=DEV)})
     bad = dict(sd)
     bad.pop("visual.norm.weight")
     from keep_b200 import KEEPConfig, KEEPModel
