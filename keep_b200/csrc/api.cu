@@ -697,6 +697,16 @@ int keepb200_prompt_scores(const float* feats, int64_t N, int64_t D, const float
   if (K == 0) return KB_OK;
   if (!feats || !cls || !scores || N <= 0 || K < 0 || C < 2 || D <= 0) return set_error(KB_ERR_ARG, "prompt_scores: bad arguments");
   const int64_t P = K * C;
+  // KEEPB200_SCREEN_FUSED=1: the top-2 margin is reduced inside the similarity epilogue and the [N, K*C] logits are never
+  // written (workspace: classifier copy + 16 B per tile and classifier instead of 4 B per tile and column). Measured
+  // SLOWER than the logits round trip (50k x 1782 x 4: 1.69 ms vs 1.49 ms; 10k x 1386 x 2: 0.24 vs 0.17 ms): the four
+  // epilogue warps become the bottleneck, so it is an opt-in for memory-constrained callers, not the default.
+  const char* fused_env = std::getenv("KEEPB200_SCREEN_FUSED");
+  if (fused_env && fused_env[0] == '1' && (C == 2 || C == 4 || C == 8 || C == 16) && D % 32 == 0 && P < (1 << 30) &&
+      workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(feats) & 15) == 0 && workspace_bytes >= prompt_scores_fused_workspace_bytes(N, D, K, C))
+    return launch_prompt_scores_fused(feats, N, (int)D, cls, (int)K, (int)C, scores, workspace, workspace_bytes,
+                                      static_cast<cudaStream_t>(stream));
   const size_t row_bytes = (size_t)P * 4;
   const size_t clsT_bytes = (size_t)P * D * 4;
   if (!workspace || workspace_bytes < clsT_bytes + row_bytes * 64)

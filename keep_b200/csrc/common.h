@@ -132,7 +132,12 @@ int launch_bert_embed(const int64_t* ids, const int64_t* tts, int64_t id_stride,
 int launch_similarity(const float* feats, int64_t N, int D, const float* cls, int P, int group, float temp,
                       float* logits, float* probs, cudaStream_t stream, float* clsT_scratch = nullptr);
 int launch_similarity_tc(const float* feats, int64_t N, int D, const float* clsT, int P, int group, float temp,
-                         float* logits, float* probs, bool* fused_probs, cudaStream_t stream);
+                         float* logits, float* probs, bool* fused_probs, cudaStream_t stream, float* score_part = nullptr);
+// fused prompt screening: scores[k] = mean_n(top1 - top2 - |top1 + top2 - 1|) over the C columns of classifier k, with the
+// margin term reduced inside the similarity epilogue (C in {2,4,8,16}, D % 32 == 0). part: [ceil(N/128)*4, K] floats.
+size_t prompt_scores_fused_workspace_bytes(int64_t N, int64_t D, int64_t K, int64_t C);
+int launch_prompt_scores_fused(const float* feats, int64_t N, int D, const float* cls, int K, int C, float* scores,
+                               void* ws, size_t ws_bytes, cudaStream_t stream);
 // scores[k] += sum_n(top1 - top2 - |top1 + top2 - 1|) over logits[n, k*C:(k+1)*C]  (scale by 1/N afterwards)
 int launch_prompt_score_accum(const float* logits, int64_t rows, int K, int C, float* scores, cudaStream_t stream);
 int launch_scale(float* v, int64_t n, float s, cudaStream_t stream);

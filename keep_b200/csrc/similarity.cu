@@ -172,6 +172,44 @@ int launch_similarity(const float* feats, int64_t N, int D, const float* cls, in
   return KB_OK;
 }
 
+// scores[k] = (sum over the row-block partials) / N : fixed order, no atomics
+__global__ void score_reduce_kernel(const float* __restrict__ part, long long nparts, int K, float inv_n, float* __restrict__ scores) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  long long i = 0;
+  for (; i + 3 < nparts; i += 4) {
+    a0 += part[i * K + k]; a1 += part[(i + 1) * K + k]; a2 += part[(i + 2) * K + k]; a3 += part[(i + 3) * K + k];
+  }
+  for (; i < nparts; ++i) a0 += part[i * K + k];
+  scores[k] = ((a0 + a1) + (a2 + a3)) * inv_n;
+}
+
+size_t prompt_scores_fused_workspace_bytes(int64_t N, int64_t D, int64_t K, int64_t C) {
+  if (N <= 0 || D <= 0 || K <= 0 || C <= 0) return 0;
+  const size_t clsT = ((size_t)K * C * D * 4 + 1023) / 1024 * 1024;
+  return clsT + (size_t)((N + 127) / 128) * 4 * K * 4;
+}
+
+int launch_prompt_scores_fused(const float* feats, int64_t N, int D, const float* cls, int K, int C, float* scores,
+                               void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const int P = K * C;
+  if (ws == nullptr || ws_bytes < prompt_scores_fused_workspace_bytes(N, D, K, C))
+    return set_error(KB_ERR_WORKSPACE, "prompt_scores: workspace too small for the fused path");
+  float* clsT = static_cast<float*>(ws);
+  float* part = reinterpret_cast<float*>(static_cast<char*>(ws) + ((size_t)P * D * 4 + 1023) / 1024 * 1024);
+  int rc = launch_transpose_f32(cls, clsT, D, P, stream);
+  if (rc) return rc;
+  bool fused = false;
+  rc = launch_similarity_tc(feats, N, D, clsT, P, C, 1.0f, nullptr, nullptr, &fused, stream, part);
+  if (rc) return rc;
+  const long long nparts = ((N + 127) / 128) * 4;
+  score_reduce_kernel<<<(unsigned)((K + 127) / 128), 128, 0, stream>>>(part, nparts, K, 1.0f / (float)N, scores);
+  note_launch();
+  KB_CUDA_CHECK(cudaGetLastError());
+  return KB_OK;
+}
+
 int launch_prompt_score_accum(const float* logits, int64_t rows, int K, int C, float* scores, cudaStream_t stream) {
   if (rows <= 0 || K <= 0) return KB_OK;
   if (C < 2) return set_error(KB_ERR_ARG, "prompt scores: need at least 2 classes per classifier (got %d)", C);

@@ -31,6 +31,7 @@ struct SimParams {
   float temp;
   float* logits;
   float* probs;
+  float* score_part;  // prompt screening: [ceil(N/128)*4, P/group] partial sums of the top-2 margin term, or null
   uint32_t idesc;
 };
 
@@ -191,6 +192,50 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
         tmem_ld_32x16(t_row + c0, v);
         tmem_ld_wait();
         const int col = n_blk * p.BN + c0;
+        if (p.score_part != nullptr) {
+          // prompt screening (WSI_evaluation/utils.py:107-117, rank_cls_score): per classifier (group of C columns) the
+          // term top1 - top2 - |top1 + top2 - 1| of every tile, summed over the 32 rows of this warp; the [N, K*C] logits
+          // never leave the SM. Whole warp participates (rows beyond N contribute 0); groups never straddle a block.
+          if (col >= p.P) continue;  // warp-uniform
+          const int G = p.group, ng = 16 / G;
+          const bool row_ok = row < p.N;
+          float term[8];
+#pragma unroll
+          for (int gi = 0; gi < 8; ++gi) {
+            float t1 = -INFINITY, t2 = -INFINITY;
+            if (gi < ng) {
+              for (int i = 0; i < G; ++i) {
+                const float x = __uint_as_float(v[gi * G + i]) * inv;
+                t2 = fmaxf(t2, fminf(t1, x));
+                t1 = fmaxf(t1, x);
+              }
+            }
+            term[gi] = (gi < ng && row_ok && col + gi * G < p.P) ? (t1 - t2) - fabsf(t1 + t2 - 1.0f) : 0.f;
+          }
+          // sum over the 32 rows of the warp: exchange-and-add butterfly over lane bits 0-2 (7 shuffles leave lane l with
+          // the 8-lane partial of group l & 7), then two plain steps over bits 3-4: 9 shuffles instead of 8 x 5
+          {
+            const bool b1 = (lane & 1) != 0, b2 = (lane & 2) != 0, b4 = (lane & 4) != 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // bit 2 of the group index: lanes with bit 2 set keep groups 4..7
+              const float keep = b4 ? term[k + 4] : term[k], send = b4 ? term[k] : term[k + 4];
+              term[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {  // bit 1
+              const float keep = b2 ? term[k + 2] : term[k], send = b2 ? term[k] : term[k + 2];
+              term[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            const float keep = b1 ? term[1] : term[0], send = b1 ? term[0] : term[1];
+            float t = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 8);
+            t += __shfl_xor_sync(0xffffffffu, t, 16);
+            const int gi = lane & 7;  // = (bit2, bit1, bit0) of the group this lane ended up with
+            if (lane < 8 && gi < ng && col + gi * G < p.P)
+              p.score_part[((long long)m_blk * 4 + q) * (p.P / G) + (col / G + gi)] = t;
+          }
+          continue;
+        }
         if (row >= p.N || col >= p.P) continue;
         float f[16];
 #pragma unroll
@@ -247,8 +292,10 @@ sim_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant_
 // clsT: fp32 [P, D] (classifier transposed to K-major). Returns KB_ERR_ARG if the shape is not supported
 // (caller falls back to the FMA kernel); *fused_probs tells whether probs were produced here.
 int launch_similarity_tc(const float* feats, int64_t N, int D, const float* clsT, int P, int group, float temp,
-                         float* logits, float* probs, bool* fused_probs, cudaStream_t stream) {
+                         float* logits, float* probs, bool* fused_probs, cudaStream_t stream, float* score_part) {
   *fused_probs = false;
+  if (score_part != nullptr && (group < 2 || group > 16 || 16 % group != 0 || P % group != 0))
+    return set_error(KB_ERR_ARG, "similarity_tc: fused screening needs a group size of 2, 4, 8 or 16 (got %d)", group);
   if (D % SBK != 0) return set_error(KB_ERR_ARG, "similarity_tc: D=%d not a multiple of 32", D);
   int BN = P >= 256 ? 256 : (P + 15) / 16 * 16;
   const int b_bytes = BN * 128;
@@ -268,7 +315,7 @@ int launch_similarity_tc(const float* feats, int64_t N, int D, const float* clsT
   }
   SimParams p;
   p.N = N; p.D = D; p.P = P; p.BN = BN; p.stages = stages; p.group = group; p.temp = temp;
-  p.logits = logits; p.probs = probs;
+  p.logits = logits; p.probs = probs; p.score_part = score_part;
   p.idesc = make_idesc(kFmtTF32, SBM, BN);
   *fused_probs = probs != nullptr && (16 % group) == 0;
   if (probs != nullptr && !*fused_probs) p.probs = nullptr;

@@ -185,8 +185,8 @@ def prompt_scores(feats, cls, K, C, workspace_mb=256):
     assert cls.shape == (D, K * C)
     scores = torch.empty(K, dtype=torch.float32, device=feats.device)
     L = _lib.lib()
-    full = L.keepb200_prompt_scores_workspace_bytes(N, D, K, C)
-    minimum = L.keepb200_prompt_scores_workspace_bytes(64, D, K, C)
+    full = L.keepb200_prompt_scores_workspace_bytes(N, D, K, C)     # classifier copy + all logits
+    minimum = L.keepb200_prompt_scores_workspace_bytes(64, D, K, C)  # ... + 64 rows of logits (chunked)
     ws_bytes = max(minimum, min(full, (workspace_mb << 20) + minimum))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device)
     _lib.check(

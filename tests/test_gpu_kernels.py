@@ -218,17 +218,38 @@ def test_similarity_and_group_softmax(tensor_cores):
     assert torch.equal(lg, torch.zeros(5, 2, device=DEV)) and (pr - 0.5).abs().max().item() < 1e-6
 
 
+def _screen_ref(feats, cls, K, C):
+    lg = (F.normalize(feats.double(), dim=-1) @ cls.double()).view(feats.shape[0], K, C)
+    top = lg.topk(2, dim=2).values
+    return ((top[..., 0] - top[..., 1]) - (top[..., 0] + top[..., 1] - 1).abs()).mean(0).float()
+
+
 def test_prompt_scores_chunked():
+    """The default path: similarity GEMM -> logits chunk -> top-2 margin reduction, several row chunks."""
     from keep_b200 import ops
 
     N, K, C = 3000, 70, 4
     feats = torch.randn(N, 768, device=DEV)
     cls = F.normalize(torch.randn(768, K * C, device=DEV), dim=0)
     s = ops.prompt_scores(feats, cls, K, C, workspace_mb=1)  # forces several row chunks
-    lg = (F.normalize(feats, dim=-1) @ cls).view(N, K, C)
-    top = lg.topk(2, dim=2).values
-    ref = ((top[..., 0] - top[..., 1]) - (top[..., 0] + top[..., 1] - 1).abs()).mean(0)
-    assert (s - ref).abs().max().item() < 1e-4
+    assert (s - _screen_ref(feats, cls, K, C)).abs().max().item() < 1e-4
+    s3 = ops.prompt_scores(feats, cls[:, :69].contiguous(), 23, 3)  # a class count that does not divide 16
+    assert (s3 - _screen_ref(feats, cls[:, :69], 23, 3)).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("N,K,C", [(3000, 70, 4), (10_000, 1386, 2), (777, 5, 2), (4097, 33, 8), (130, 3, 16)])
+def test_prompt_scores_fused_epilogue(N, K, C, monkeypatch):
+    """KEEPB200_SCREEN_FUSED=1: the top-2 margin reduced inside the similarity epilogue (utils.py:107-130 in one kernel,
+    no [N, K*C] logits in memory): ragged row counts, ragged column tiles, every supported class count; deterministic."""
+    from keep_b200 import ops
+
+    monkeypatch.setenv("KEEPB200_SCREEN_FUSED", "1")
+    g = torch.Generator(device=DEV).manual_seed(N + K)
+    feats = torch.randn(N, 768, device=DEV, generator=g) * 2
+    cls = F.normalize(torch.randn(768, K * C, device=DEV, generator=g), dim=0)
+    s = ops.prompt_scores(feats, cls, K, C)
+    assert (s - _screen_ref(feats, cls, K, C)).abs().max().item() < 1e-4
+    assert torch.equal(s, ops.prompt_scores(feats, cls, K, C))
 
 
 @pytest.mark.parametrize("overlap", [True, False])
