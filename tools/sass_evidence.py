@@ -18,7 +18,7 @@ for line in out.splitlines():
         cur = m.group(1)
         funcs[cur] = collections.Counter()
         continue
-    m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line) if cur else None
+    m = re.search(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line) if cur else None
     if m:
         for k in keys[:-1]:
             if m.group(1).startswith(k):
