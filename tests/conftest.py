@@ -29,3 +29,14 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _seeded():
+    """Every test starts from the same RNG state (CPU and CUDA): tolerances are never exercised on a lucky/unlucky draw."""
+    import torch
+
+    torch.manual_seed(20260117)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(20260117)
+    yield
