@@ -25,7 +25,8 @@
  *     keepb200_last_error() returns a thread-local message for the last failing call;
  *   - one handle per device and per thread of control (a handle is not thread-safe);
  *   - after keepb200_finalize() the library performs no hidden allocations: activations live in the
- *     workspace the caller passes, sized by keepb200_workspace_bytes().
+ *     workspace the caller passes, sized by keepb200_workspace_bytes();
+ *   - no environment variable changes what is computed: numerics are selected by arguments only.
  *   - there is no CPU fallback anywhere: without a CUDA device of compute capability 10.x every
  *     compute entry point fails.
  */
@@ -39,7 +40,7 @@
 extern "C" {
 #endif
 
-#define KEEPB200_ABI_VERSION 1
+#define KEEPB200_ABI_VERSION 2
 
 #define KEEPB200_OK 0
 #define KEEPB200_ERR_ARG (-1)
@@ -54,6 +55,16 @@ extern "C" {
 /* tile layouts accepted by keepb200_encode_image */
 #define KEEPB200_TILES_F32_NCHW 0 /* float [B,3,H,W], already ImageNet-normalised (keep_inference.py:88-93) */
 #define KEEPB200_TILES_U8_NHWC 1  /* uint8 [B,H,W,3] raw RGB; ToTensor+Normalize fused into the patch gather */
+
+/* precision of keepb200_encode_text. HIGH: every GEMM of the text tower runs split-operand (activations and weights as
+ * hi + lo 16-bit pairs, three tensor-core passes into the same fp32 accumulator): ~3e-4 rel-L2 against the fp32 reference
+ * instead of ~1.4e-3, at three times the MMA work - nothing for the few thousand prompts of a WSI classifier bank.
+ * FAST: one pass (prompt banks of 1e5 prompts). AUTO: HIGH when the call encodes at most
+ * KEEPB200_TEXT_AUTO_MAX_PROMPTS prompts, FAST otherwise (a function of P only). */
+#define KEEPB200_TEXT_AUTO 0
+#define KEEPB200_TEXT_HIGH 1
+#define KEEPB200_TEXT_FAST 2
+#define KEEPB200_TEXT_AUTO_MAX_PROMPTS 8192
 
 /* ops for keepb200_workspace_bytes */
 #define KEEPB200_OP_ENCODE_IMAGE 0
@@ -132,7 +143,7 @@ int keepb200_preprocess_u8(const uint8_t* tiles, int64_t B, int64_t H, int64_t W
  * zeros / ones). `s_eff` (1..S) is the number of leading positions to compute: positions >= s_eff must be
  * masked in every row, in which case the result is identical to the padded computation; pass S to disable. */
 int keepb200_encode_text(void* handle, const int64_t* ids, const int64_t* type_ids, const int64_t* mask, int64_t P,
-                         int64_t S, int64_t s_eff, float* out, void* workspace, size_t workspace_bytes,
+                         int64_t S, int64_t s_eff, int precision, float* out, void* workspace, size_t workspace_bytes,
                          void* stream);
 
 /* ---- similarity (no handle) ------------------------------------------------------------------------ */
@@ -148,10 +159,14 @@ int keepb200_similarity(const float* feats, int64_t N, int64_t D, const float* c
 size_t keepb200_similarity_workspace_bytes(int64_t D, int64_t P);
 
 /* Prompt screening (utils.py:107-146): for K classifiers of C classes stacked as cls[D, K*C], with
- * logits_k = normalize(feats) @ cls_k: scores[k] = mean_n( top1 - top2 - |top1 + top2 - 1| ). */
-int keepb200_prompt_scores(const float* feats, int64_t N, int64_t D, const float* cls, int64_t K, int64_t C,
+ * logits_k = normalize(feats) @ cls_k: scores[k] = mean_n( top1 - top2 - |top1 + top2 - 1| ). The reduction over tiles
+ * runs in a fixed order (per-256-row partials, then one ordered sum): scores are bit-identical from run to run.
+ * fused != 0 (C in {2,4,8,16}, D % 32 == 0): the margin is reduced inside the similarity epilogue and the [N, K*C]
+ * logits never reach memory - less workspace, measured slower; the caller's choice. */
+int keepb200_prompt_scores(const float* feats, int64_t N, int64_t D, const float* cls, int64_t K, int64_t C, int fused,
                            float* scores, void* workspace, size_t workspace_bytes, void* stream);
-/* minimum workspace: K*C*D*4 (K-major classifier copy) + 64 rows of logits; more rows = fewer passes */
+/* workspace for all rows at once: K-major classifier copy + score partials + N rows of logits; the call also accepts
+ * less (down to 64 rows of logits: keepb200_prompt_scores_workspace_bytes(64, ...) + partials for N) and then chunks */
 size_t keepb200_prompt_scores_workspace_bytes(int64_t N, int64_t D, int64_t K, int64_t C);
 
 /* refine_seg (detection_utils.py:39-74 et al.): coords int64 [N,2] (x,y), probs fp32 [N,C].
@@ -173,6 +188,15 @@ int keepb200_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_laun
 /* Per-shape summary of the last profile_end(): "M,N,K,epi,launches,ms,TFLOP/s;" records (host string). */
 const char* keepb200_profile_table(void);
 
+/* ---- test / analysis hooks ----------------------------------------------------------------------------------------- */
+/* LayerNorm placement in the ViT blocks: 0 stand-alone LayerNorm kernels, 1 (default) norm1 folded into the qkv GEMM,
+ * 2 norm2 folded into fc1 as well. The parity tests run all three against the oracle. */
+int keepb200_debug_set_ln_fuse(void* handle, int mode);
+/* Per-layer residual-stream dump of the following encode_image / encode_text calls (each call must fit ONE workspace
+ * chunk): slot i of [rows*width] floats receives the stream after block/layer i; the last slot holds the CLS rows only
+ * ([n*width] floats). buf = NULL switches it off. Used by the per-layer parity table (tests/test_gpu_model.py). */
+int keepb200_debug_layer_dump(void* handle, float* buf, size_t bytes);
+
 /* ---- single-kernel entry points (unit tests and profiling) ------------------------------------------- */
 /* out = epilogue(A[M,K] . W[N,K]^T); epi: 0 bias->16-bit, 1 bias+GELU(erf)->16-bit,
  * 2 resid + gamma*(acc+bias) -> fp32, 3 bias -> fp32, 4 ViT patch-embed scatter (+pos) -> fp32 */
@@ -193,10 +217,27 @@ int keepb200_op_fold_ln(const float* W, int N, int K, const float* lnw, const fl
                         int bf16, float* s, float* c, void* stream);
 /* pos_embed [1 + G0*G0, D] -> out [1 + Gh*Gw, D] (timm resample_abs_pos_embed: bicubic, antialias=True, 1 prefix token) */
 int keepb200_op_pos_resample(const float* pos, int G0, int Gh, int Gw, int D, float* out, void* stream);
+/* y16 rows have pitch y16_pitch (0 = D); lo_off > 0 also stores 16-bit(y - hi) at y16[i, lo_off + c] (hi|lo operand) */
 int keepb200_op_layernorm(const float* x, int64_t row_stride, int64_t rows, int D, const float* w, const float* b,
-                          float eps, void* y16, int bf16, float* y32, void* stream);
+                          float eps, void* y16, int bf16, float* y32, int64_t y16_pitch, int64_t lo_off, void* stream);
+/* out rows have pitch out_pitch (0 = H*64); lo_off > 0 also stores the rounding remainder of the context */
 int keepb200_op_attention(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
-                          int64_t mask_stride, float scale, void* stream);
+                          int64_t mask_stride, float scale, int64_t out_pitch, int64_t lo_off, void* stream);
+/* Split-operand GEMM (csrc/common.h GEMM_SPLIT_*): split 0 plain, 1 W = [N,2K] hi|lo (2 passes), 2 A = [M,2K] and
+ * W = [N,2K] hi|lo (3 passes: Ah.Wh + Al.Wh + Ah.Wl). epi 8 = bias + GELU(erf) -> [hi | lo] output, lo at lo_off.
+ * op_cast_hilo builds a hi|lo operand from fp32: dst[r, 0:K] = 16-bit(src), dst[r, K:2K] = 16-bit(src - hi). */
+int keepb200_op_gemm_split(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int epi, int bf16,
+                           int split, const float* bias, const float* resid, int64_t ldr, void* out, int64_t ldo,
+                           int64_t lo_off, void* stream);
+int keepb200_op_cast_hilo(const float* src, void* dst, int64_t rows, int K, int bf16, void* stream);
+/* Fused fp32 tails (csrc/head.cu), weights TRANSPOSED ([K, N] fp32):
+ *   op_visual_head: out = normalize(W1 . gelu(W0 . LayerNorm(x) + b0) + b1)      keep_inference.py:42-46, 54-58
+ *   op_pooler:      out = normalize(tanh(W . x + b))                              keep_inference.py:60-62 */
+int keepb200_op_visual_head(const float* x, int64_t ldx, int64_t n, int D, const float* lnw, const float* lnb, float eps,
+                            const float* w0t, const float* b0, int N0, const float* w1t, const float* b1, int N1, float* out,
+                            void* stream);
+int keepb200_op_pooler(const float* x, int64_t ldx, int64_t n, int D, const float* wt, const float* b, float* out,
+                       void* stream);
 /* Debug/profiling aid: when dev_buf (device int64 [64*16]) is non-NULL the tcgen05 attention kernel's CTA 0 records
  * clock64() stamps of its pipeline events for its first 64 work units; NULL switches tracing off. */
 int keepb200_debug_attention_trace(int64_t* dev_buf);

@@ -63,11 +63,11 @@ SIGNATURES = {
     "keepb200_encode_image_hw": (_int, [_p, _p, _int, _i64, _i64, _i64, _p, _p, _sz, _p]),
     "keepb200_preprocess_workspace_bytes": (_sz, [_i64, _i64, _i64, _int]),
     "keepb200_preprocess_u8": (_int, [_p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
-    "keepb200_encode_text": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _p, _p, _sz, _p]),
+    "keepb200_encode_text": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
     "keepb200_similarity": (_int, [_p, _i64, _i64, _p, _i64, _int, _f, _p, _p, _p, _sz, _p]),
     "keepb200_similarity_workspace_bytes": (_sz, [_i64, _i64]),
     "keepb200_prompt_scores_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
-    "keepb200_prompt_scores": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _p, _sz, _p]),
+    "keepb200_prompt_scores": (_int, [_p, _i64, _i64, _p, _i64, _i64, _int, _p, _p, _sz, _p]),
     "keepb200_refine": (_int, [_p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _sz, _p]),
     "keepb200_refine_workspace_bytes": (_sz, [_i64]),
     "keepb200_launch_count": (_i64, []),
@@ -79,11 +79,20 @@ SIGNATURES = {
     "keepb200_op_gemm_ln": (_int, [_p, _p, _int, _int, _int, _int, _int, _p, _p, _p, _f, _p, _p]),
     "keepb200_op_fold_ln": (_int, [_p, _int, _int, _p, _p, _p, _p, _int, _p, _p, _p]),
     "keepb200_op_pos_resample": (_int, [_p, _int, _int, _int, _int, _p, _p]),
-    "keepb200_op_layernorm": (_int, [_p, _i64, _i64, _int, _p, _p, _f, _p, _int, _p, _p]),
-    "keepb200_op_attention": (_int, [_p, _p, _int, _int, _int, _int, _p, _i64, _f, _p]),
+    "keepb200_op_layernorm": (_int, [_p, _i64, _i64, _int, _p, _p, _f, _p, _int, _p, _i64, _i64, _p]),
+    "keepb200_op_attention": (_int, [_p, _p, _int, _int, _int, _int, _p, _i64, _f, _i64, _i64, _p]),
+    "keepb200_op_gemm_split": (_int, [_p, _i64, _p, _i64, _int, _int, _int, _int, _int, _int, _p, _p, _i64, _p, _i64, _i64, _p]),
+    "keepb200_op_cast_hilo": (_int, [_p, _p, _i64, _int, _int, _p]),
+    "keepb200_op_visual_head": (_int, [_p, _i64, _i64, _int, _p, _p, _f, _p, _p, _int, _p, _p, _int, _p, _p]),
+    "keepb200_op_pooler": (_int, [_p, _i64, _i64, _int, _p, _p, _p, _p]),
+    "keepb200_debug_set_ln_fuse": (_int, [_p, _int]),
+    "keepb200_debug_layer_dump": (_int, [_p, _p, _sz]),
     "keepb200_debug_attention_trace": (_int, [_p]),
     "keepb200_op_act_l2norm": (_int, [_p, _i64, _int, _int, _p, _p]),
 }
+
+ABI_VERSION = 2  # KEEPB200_ABI_VERSION of include/keep_b200.h
+TEXT_AUTO, TEXT_HIGH, TEXT_FAST = 0, 1, 2
 
 _LIB = None
 
@@ -99,21 +108,28 @@ def lib() -> C.CDLL:
         return _LIB
     path = _build.LIB_PATH
     override = os.environ.get("KEEPB200_LIB")  # A/B measurements against another build of the same ABI
-    try:
-        path = Path(override) if override else _build.build()
-    except Exception as e:  # no toolkit on this box: fall through to a prebuilt in-tree library
-        if not path.exists():
-            raise KeepB200Error(
-                f"libkeep_b200.so is missing and could not be built ({e}); "
-                "keep_b200 has no CPU or PyTorch fallback"
-            ) from e
+    if override:
+        path = Path(override)
+    else:
+        # build() takes an inter-process lock around the stale check, the compile and the atomic replace of the
+        # library, so the ranks of a torchrun job never load a half-written file
+        try:
+            path = _build.build()
+        except _build.ToolchainMissing as e:  # no nvcc on this box: only a complete prebuilt in-tree library will do
+            if not path.exists():
+                raise KeepB200Error(
+                    f"libkeep_b200.so is missing and could not be built ({e}); "
+                    "keep_b200 has no CPU or PyTorch fallback"
+                ) from e
+        except Exception as e:  # a failed compile must never fall back to a stale library
+            raise KeepB200Error(f"building libkeep_b200.so failed: {e}") from e
     handle = C.CDLL(str(path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(handle, name)  # AttributeError here = header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if handle.keepb200_version() != 1:
-        raise KeepB200Error(f"ABI version mismatch: library {handle.keepb200_version()} != binding 1")
+    if handle.keepb200_version() != ABI_VERSION:
+        raise KeepB200Error(f"ABI version mismatch: library {handle.keepb200_version()} != binding {ABI_VERSION}")
     _LIB = handle
     return handle
 

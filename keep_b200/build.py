@@ -29,11 +29,15 @@ NVCC_FLAGS = [
 ]
 
 
+class ToolchainMissing(RuntimeError):
+    """nvcc is not on this box (a prebuilt in-tree library may still be usable)."""
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and Path(cand).exists():
             return cand
-    raise RuntimeError("nvcc not found: keep_b200 needs the CUDA 12.9 toolkit to build its sm_100a kernels")
+    raise ToolchainMissing("nvcc not found: keep_b200 needs the CUDA 12.9 toolkit to build its sm_100a kernels")
 
 
 def _sources() -> list[Path]:
@@ -53,35 +57,58 @@ def is_stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile (if needed) and return the path of libkeep_b200.so."""
+    """Compile (if needed) and return the path of libkeep_b200.so.
+
+    Safe to call from several processes at once (every rank of a torchrun job does): the stale check, the compile and
+    the link run under an exclusive file lock, objects and the library are written to temporary names and moved into
+    place with os.replace, so no process ever maps a half-written file."""
     if not force and not is_stale():
         return LIB_PATH
-    nvcc = _nvcc()
+    import fcntl
+
     BUILD_DIR.mkdir(exist_ok=True)
+    with open(BUILD_DIR / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():  # another process built it while this one waited
+                return LIB_PATH
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
+    nvcc = _nvcc()
     hdr_m = _deps_mtime()
 
     def compile_one(src: Path) -> Path:
         obj = BUILD_DIR / (src.stem + ".o")
         if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, hdr_m):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE_DIR), "-c", str(src), "-o", str(obj)]
+        tmp = obj.with_suffix(f".o.tmp{os.getpid()}")
+        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE_DIR), "-c", str(src), "-o", str(tmp)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
+            tmp.unlink(missing_ok=True)
             raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
         if verbose:
             print(r.stderr, flush=True)
+        os.replace(tmp, obj)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
     # the CUDA runtime is linked statically (nvcc default): no libcudart/libcuda lookup at load time
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *map(str, objs)]
+    tmp_lib = LIB_PATH.with_suffix(f".so.tmp{os.getpid()}")
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp_lib), *map(str, objs)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        tmp_lib.unlink(missing_ok=True)
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp_lib, LIB_PATH)
     return LIB_PATH
 
 

@@ -18,13 +18,18 @@ DEFAULT_VISION_CONFIG = dict(img_size=224, patch_size=16, width=1024, depth=24, 
 class KEEPConfig(PretrainedConfig):
     model_type = "keep"
 
-    def __init__(self, vision_config=None, text_config=None, projection_dim=768, operand_dtype="float16", **kwargs):
+    def __init__(self, vision_config=None, text_config=None, projection_dim=768, operand_dtype="float16",
+                 text_precision="auto", **kwargs):
         super().__init__(**kwargs)
         self.vision_config = vision_config
         self.text_config = text_config
         self.projection_dim = projection_dim
-        # keep_b200 extension: 16-bit type of the tensor-core operands ("float16" | "bfloat16")
+        # keep_b200 extensions.  operand_dtype: 16-bit type of the tensor-core operands ("float16" | "bfloat16").
+        # text_precision: "high" = split-operand GEMMs through the whole text tower (hi + lo 16-bit pairs, ~3e-4 rel-L2
+        # against the fp32 reference, three MMA passes), "fast" = one pass (~1.4e-3), "auto" = high for calls of up to
+        # 8192 prompts (every WSI classifier bank), fast for larger prompt banks.
         self.operand_dtype = operand_dtype
+        self.text_precision = text_precision
 
     # resolved geometry ---------------------------------------------------------------------------
     def vision(self) -> dict:

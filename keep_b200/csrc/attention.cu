@@ -15,8 +15,6 @@
 #include "common.h"
 #include "ptx.cuh"
 
-#include <cstdlib>
-#include <cstring>
 
 namespace kb {
 namespace {
@@ -67,13 +65,20 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
+template <bool BF16>
+__device__ __forceinline__ float2 unpack2(uint32_t v) {
+  if constexpr (BF16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+  else return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
+
 // row r, 16-byte chunk c (0..7) of a [rows][64 x 16-bit] tile, XOR-swizzled against bank conflicts
 __device__ __forceinline__ uint32_t sw_off(int r, int c) { return uint32_t(r) * 128u + uint32_t((c ^ (r & 7)) << 4); }
 
 template <bool BF16>
 __global__ void __launch_bounds__(kAttThreads)
 attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, int S, int H,
-                 const long long* __restrict__ key_mask, long long mask_stride, float scale_log2) {
+                 const long long* __restrict__ key_mask, long long mask_stride, float scale_log2, long long ldo,
+                 long long lo_off) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int spad = (S + KB_ - 1) / KB_ * KB_;
   uint8_t* sK = smem;
@@ -216,45 +221,47 @@ attention_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ out, i
   const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
   const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
   const int row_a = r0 + (lane >> 2), row_b = row_a + 8;
-  const long long ldo = (long long)H * DH;
   uint16_t* ob = out + (long long)b * S * ldo + h * DH + (lane & 3) * 2;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    if (row_a < S) *reinterpret_cast<uint32_t*>(ob + row_a * ldo + nt * 8) = pack2<BF16>(o[nt][0] * inv0, o[nt][1] * inv0);
-    if (row_b < S) *reinterpret_cast<uint32_t*>(ob + row_b * ldo + nt * 8) = pack2<BF16>(o[nt][2] * inv1, o[nt][3] * inv1);
+    const float a0 = o[nt][0] * inv0, a1 = o[nt][1] * inv0, b0 = o[nt][2] * inv1, b1 = o[nt][3] * inv1;
+    const uint32_t ha = pack2<BF16>(a0, a1), hb = pack2<BF16>(b0, b1);
+    if (row_a < S) *reinterpret_cast<uint32_t*>(ob + row_a * ldo + nt * 8) = ha;
+    if (row_b < S) *reinterpret_cast<uint32_t*>(ob + row_b * ldo + nt * 8) = hb;
+    if (lo_off > 0) {  // rounding remainder of the context: the output projection then runs as a split-operand GEMM
+      const float2 fa = unpack2<BF16>(ha), fb = unpack2<BF16>(hb);
+      if (row_a < S) *reinterpret_cast<uint32_t*>(ob + row_a * ldo + lo_off + nt * 8) = pack2<BF16>(a0 - fa.x, a1 - fa.y);
+      if (row_b < S) *reinterpret_cast<uint32_t*>(ob + row_b * ldo + lo_off + nt * 8) = pack2<BF16>(b0 - fb.x, b1 - fb.y);
+    }
   }
 }
 
 }  // namespace
 
 int launch_attention(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
-                     int64_t mask_stride, float scale, cudaStream_t stream) {
+                     int64_t mask_stride, float scale, cudaStream_t stream, int64_t out_pitch, int64_t lo_off) {
   if (B <= 0 || S <= 0 || H <= 0) return KB_OK;
-  static int force_v1 = -1;
-  if (force_v1 < 0) {
-    const char* e = std::getenv("KEEPB200_ATTN");
-    force_v1 = (e && !std::strcmp(e, "v1")) ? 1 : 0;
-  }
-  if (attention_tc_supports(S) && !force_v1) return launch_attention_tc(qkv, out, B, S, H, bf16, key_mask, mask_stride, scale, stream);
+  if (out_pitch <= 0) out_pitch = (int64_t)H * DH;
+  if (out_pitch % 8 != 0 || lo_off % 8 != 0 || (lo_off > 0 && lo_off + (int64_t)H * DH > out_pitch))
+    return set_error(KB_ERR_ARG, "attention: output pitch %lld / lo offset %lld invalid", (long long)out_pitch, (long long)lo_off);
+  if (attention_tc_supports(S) && lo_off == 0 && out_pitch == (int64_t)H * DH)
+    return launch_attention_tc(qkv, out, B, S, H, bf16, key_mask, mask_stride, scale, stream);
   if (S > 512) return set_error(KB_ERR_ARG, "attention: S=%d > 512 unsupported", S);
   const int spad = (S + KB_ - 1) / KB_ * KB_;
   const int smem = (2 * spad + QB) * 128 + spad * 4;
-  static int smem_set[2] = {0, 0};
-  if (smem > smem_set[bf16 ? 1 : 0]) {
-    if (bf16)
-      KB_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    else
-      KB_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    smem_set[bf16 ? 1 : 0] = smem;
-  }
   const unsigned grid = (unsigned)((S + QB - 1) / QB) * H * B;
   const float scale_log2 = scale * 1.4426950408889634f;
-  if (bf16)
+  if (bf16) {
+    KB_TRY_ATTR(attention_kernel<true>, smem);
     attention_kernel<true><<<grid, kAttThreads, smem, stream>>>((const uint16_t*)qkv, (uint16_t*)out, S, H,
-                                                                (const long long*)key_mask, mask_stride, scale_log2);
-  else
+                                                                (const long long*)key_mask, mask_stride, scale_log2,
+                                                                out_pitch, lo_off);
+  } else {
+    KB_TRY_ATTR(attention_kernel<false>, smem);
     attention_kernel<false><<<grid, kAttThreads, smem, stream>>>((const uint16_t*)qkv, (uint16_t*)out, S, H,
-                                                                 (const long long*)key_mask, mask_stride, scale_log2);
+                                                                 (const long long*)key_mask, mask_stride, scale_log2,
+                                                                 out_pitch, lo_off);
+  }
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;

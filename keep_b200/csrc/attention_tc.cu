@@ -426,12 +426,8 @@ int launch_attention_tc(const void* qkv, void* out, int B, int S, int H, int bf1
   if (rc) return rc;
   rc = get_tmap_2d(qkv, dt, rows, cols, cols, S_pad, &tkv);
   if (rc) return rc;
-  static bool attr_set = false;
   const int smem = Smem::total + 1024;
-  if (!attr_set) {
-    KB_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  KB_TRY_ATTR(attention_tc_kernel, smem);
   AtcParams p;
   p.B = B; p.S = S; p.H = H; p.S_pad = S_pad; p.n_qt = (S + 127) / 128; p.items = B * H;
   p.key_mask = reinterpret_cast<const long long*>(key_mask);

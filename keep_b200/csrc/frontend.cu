@@ -11,6 +11,10 @@
 namespace kb {
 namespace {
 
+__device__ __forceinline__ float2 unpk(uint32_t v, int bf16) {
+  if (bf16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+  return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
 __device__ __forceinline__ uint32_t pk(float a, float b, int bf16) {
   if (bf16) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -151,7 +155,8 @@ __global__ void __launch_bounds__(256)
 bert_embed_kernel(const long long* __restrict__ ids, const long long* __restrict__ tts, long long id_stride,
                   long long rows, int S, const float* __restrict__ word, const float* __restrict__ type,
                   const float* __restrict__ pos, const float* __restrict__ lnw, const float* __restrict__ lnb, float eps,
-                  float* __restrict__ x32, uint16_t* __restrict__ x16, int bf16, int vocab, int type_vocab) {
+                  float* __restrict__ x32, uint16_t* __restrict__ x16, int bf16, int vocab, int type_vocab,
+                  long long x16_pitch, long long lo_off) {
   constexpr int D = NV * 128;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -195,7 +200,14 @@ bert_embed_kernel(const long long* __restrict__ ids, const long long* __restrict
     uint2 h;
     h.x = pk(o.x, o.y, bf16);
     h.y = pk(o.z, o.w, bf16);
-    *reinterpret_cast<uint2*>(x16 + row * D + (lane + 32 * i) * 4) = h;
+    *reinterpret_cast<uint2*>(x16 + row * x16_pitch + (lane + 32 * i) * 4) = h;
+    if (lo_off > 0) {  // rounding remainder for the split-operand GEMMs
+      const float2 a = unpk(h.x, bf16), b = unpk(h.y, bf16);
+      uint2 l;
+      l.x = pk(o.x - a.x, o.y - a.y, bf16);
+      l.y = pk(o.z - b.x, o.w - b.y, bf16);
+      *reinterpret_cast<uint2*>(x16 + row * x16_pitch + lo_off + (lane + 32 * i) * 4) = l;
+    }
   }
 }
 
@@ -248,15 +260,19 @@ int launch_im2col_u8(const uint8_t* tiles, int64_t B, int Gh, int G, void* patch
 
 int launch_bert_embed(const int64_t* ids, const int64_t* tts, int64_t id_stride, int64_t P, int S, int D,
                       const float* word, const float* type, const float* pos, const float* lnw, const float* lnb,
-                      float eps, float* x32, void* x16, int bf16, int vocab, int type_vocab, cudaStream_t stream) {
+                      float eps, float* x32, void* x16, int bf16, int vocab, int type_vocab, cudaStream_t stream,
+                      int64_t x16_pitch, int64_t lo_off) {
   const long long rows = (long long)P * S;
   if (rows <= 0) return KB_OK;
   if (D % 128 != 0 || D > 1024) return set_error(KB_ERR_ARG, "bert_embed: hidden=%d unsupported", D);
+  if (x16_pitch <= 0) x16_pitch = D;
+  if (x16_pitch % 4 != 0 || lo_off % 4 != 0 || (lo_off > 0 && lo_off + D > x16_pitch))
+    return set_error(KB_ERR_ARG, "bert_embed: 16-bit output pitch / lo offset invalid");
   const unsigned grid = (unsigned)((rows + 7) / 8);
 #define KB_EMB(NVV)                                                                                              \
   bert_embed_kernel<NVV><<<grid, 256, 0, stream>>>((const long long*)ids, (const long long*)tts, id_stride, rows, S, \
                                                    word, type, pos, lnw, lnb, eps, x32, (uint16_t*)x16, bf16, vocab,  \
-                                                   type_vocab)
+                                                   type_vocab, x16_pitch, lo_off)
   switch (D / 128) {
     case 1: KB_EMB(1); break;
     case 2: KB_EMB(2); break;

@@ -12,7 +12,7 @@
 //     LayerScale + fp32 residual / patch-embed scatter + pos_embed).
 //
 // Two main-loop variants:
-//   gemm_kernel<BN,EPI>   one CTA per tile, UMMA 128 x BN x 16 (cta_group::1) — small problems
+//   gemm_kernel<BN,EPI>   one CTA per tile, UMMA 128 x BN x 16 (cta_group::1), BN = 128 — small problems
 //   gemm2_kernel<EPI>     a CTA PAIR (cluster of 2) per 256x256 tile, UMMA 256 x 256 x 16 (cta_group::2):
 //                         each CTA stages its 128 rows of A and its 128 rows of W, so per-SM operand traffic
 //                         (L2->SMEM and SMEM->tensor core) drops by a third against the 128x256 single-CTA tile
@@ -23,10 +23,6 @@
 #include "common.h"
 #include "ptx.cuh"
 
-#include <cstdlib>
-#include <cstring>
-#include <map>
-#include <mutex>
 
 namespace kb {
 
@@ -60,7 +56,11 @@ struct KParams {
   const float* ln_s;     // EPI_LN_*: [N] column sums of the folded weight
   int ln_slices;
   float ln_inv_width, ln_eps;
-  int prefetch;  // residual epilogues: L2-prefetch the next tile's residual block (only pays when a tile is short)
+  // split-operand mode (common.h GemmArgs::split): the K loop runs `nseg` passes over the K/64 k-blocks; pass s reads the
+  // A tile at column offset a_off[s] and the W tile at w_off[s] (0 = hi half, K = lo half of a [rows, 2K] hi|lo operand)
+  int nseg;
+  int a_off[3], w_off[3];
+  long long lo_off;  // EPI_BIAS_GELU_HILO: element offset of the lo half inside an output row
 };
 
 // Exact-erf GELU (torch.nn.GELU() default), gelu(x) = x * Phi(x), written for the epilogue's instruction budget
@@ -69,50 +69,28 @@ struct KParams {
 //   gelu(x) = relu(x) - |x| * q(|x|),   q(a) = exp2(P(a)) on [0, 6]  (q(6) = 1e-9: clamped beyond).
 // P is a weighted minimax fit of log2(0.5 erfc(a/sqrt2)), the weight being the error it causes in gelu
 // (tools/fit_gelu.py). The result is stored as a 16-bit float, whose rounding is >= 2.4e-5 for |gelu| >= 0.05:
-//   KB_GELU_DEG 4 (default): |gelu error| <= 6.6e-6 in fp32 evaluation,  7 FMA-pipe instructions + 1 MUFU
-//   KB_GELU_DEG 6          : |gelu error| <= 3.3e-7,                      9 FMA-pipe instructions + 1 MUFU
-#ifndef KB_GELU_DEG
-#define KB_GELU_DEG 4
-#endif
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float ax = fabsf(x);
-  const float m = fminf(ax, 6.0f);
-#if KB_GELU_DEG == 6
-  float p = fmaf(m, 2.904253473e-05f, -7.323236443e-04f);
-  p = fmaf(m, p, 7.953787372e-03f);
-  p = fmaf(m, p, -5.320511315e-02f);
-  p = fmaf(m, p, -4.589348205e-01f);
-  p = fmaf(m, p, -1.151144948e+00f);
-  p = fmaf(m, p, -9.999990962e-01f);
-#else
-  float p = fmaf(m, 3.920550193e-03f, -4.439129536e-02f);
-  p = fmaf(m, p, -4.674139173e-01f);
-  p = fmaf(m, p, -1.147820817e+00f);
-  p = fmaf(m, p, -1.000374045e+00f);
-#endif
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p));
-  return fmaf(-ax, e, fmaxf(x, 0.0f));
-}
-
-// Two elements at once on the packed fp32 pipe (FFMA2, sm_100): same arithmetic, same rounding per element, half the
-// FMA-pipe instructions for the polynomial and the final multiply-add.
+//   DEG 4: |gelu error| <= 6.6e-6 in fp32 evaluation,  7 FMA-pipe instructions + 1 MUFU   (16-bit outputs)
+//   DEG 6: |gelu error| <= 3.3e-7,                      9 FMA-pipe instructions + 1 MUFU   (hi|lo outputs, ~22 bits)
+// Evaluated for two elements at once on the packed fp32 pipe (FFMA2, sm_100): half the FMA-pipe instructions for the
+// polynomial and the final multiply-add.
+template <int DEG>
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
   const float2 m = make_float2(fminf(ax.x, 6.0f), fminf(ax.y, 6.0f));
-#if KB_GELU_DEG == 6
-  float2 p = __ffma2_rn(m, make_float2(2.904253473e-05f, 2.904253473e-05f), make_float2(-7.323236443e-04f, -7.323236443e-04f));
-  p = __ffma2_rn(m, p, make_float2(7.953787372e-03f, 7.953787372e-03f));
-  p = __ffma2_rn(m, p, make_float2(-5.320511315e-02f, -5.320511315e-02f));
-  p = __ffma2_rn(m, p, make_float2(-4.589348205e-01f, -4.589348205e-01f));
-  p = __ffma2_rn(m, p, make_float2(-1.151144948e+00f, -1.151144948e+00f));
-  p = __ffma2_rn(m, p, make_float2(-9.999990962e-01f, -9.999990962e-01f));
-#else
-  float2 p = __ffma2_rn(m, make_float2(3.920550193e-03f, 3.920550193e-03f), make_float2(-4.439129536e-02f, -4.439129536e-02f));
-  p = __ffma2_rn(m, p, make_float2(-4.674139173e-01f, -4.674139173e-01f));
-  p = __ffma2_rn(m, p, make_float2(-1.147820817e+00f, -1.147820817e+00f));
-  p = __ffma2_rn(m, p, make_float2(-1.000374045e+00f, -1.000374045e+00f));
-#endif
+  float2 p;
+  if constexpr (DEG == 6) {
+    p = __ffma2_rn(m, make_float2(2.904253473e-05f, 2.904253473e-05f), make_float2(-7.323236443e-04f, -7.323236443e-04f));
+    p = __ffma2_rn(m, p, make_float2(7.953787372e-03f, 7.953787372e-03f));
+    p = __ffma2_rn(m, p, make_float2(-5.320511315e-02f, -5.320511315e-02f));
+    p = __ffma2_rn(m, p, make_float2(-4.589348205e-01f, -4.589348205e-01f));
+    p = __ffma2_rn(m, p, make_float2(-1.151144948e+00f, -1.151144948e+00f));
+    p = __ffma2_rn(m, p, make_float2(-9.999990962e-01f, -9.999990962e-01f));
+  } else {
+    p = __ffma2_rn(m, make_float2(3.920550193e-03f, 3.920550193e-03f), make_float2(-4.439129536e-02f, -4.439129536e-02f));
+    p = __ffma2_rn(m, p, make_float2(-4.674139173e-01f, -4.674139173e-01f));
+    p = __ffma2_rn(m, p, make_float2(-1.147820817e+00f, -1.147820817e+00f));
+    p = __ffma2_rn(m, p, make_float2(-1.000374045e+00f, -1.000374045e+00f));
+  }
   float2 e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(p.x));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(p.y));
@@ -128,12 +106,18 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int bf16) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+__device__ __forceinline__ float2 unpack16(uint32_t v, int bf16) {
+  if (bf16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+  return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
+
 template <int EPI> struct EpiTraits {
   static constexpr bool kResid = (EPI == EPI_RESID_F32 || EPI == EPI_RESID_F32_STATS);
   static constexpr bool kStats = (EPI == EPI_RESID_F32_STATS);
   static constexpr bool kLn = (EPI == EPI_LN_BIAS_HALF || EPI == EPI_LN_BIAS_GELU_HALF);
-  static constexpr bool kGelu = (EPI == EPI_BIAS_GELU_HALF || EPI == EPI_LN_BIAS_GELU_HALF);
-  static constexpr bool kHalfOut = (EPI == EPI_BIAS_HALF || EPI == EPI_BIAS_GELU_HALF || kLn);
+  static constexpr bool kHiLo = (EPI == EPI_BIAS_GELU_HILO);
+  static constexpr bool kGelu = (EPI == EPI_BIAS_GELU_HALF || EPI == EPI_LN_BIAS_GELU_HALF || kHiLo);
+  static constexpr bool kHalfOut = (EPI == EPI_BIAS_HALF || EPI == EPI_BIAS_GELU_HALF || kLn || kHiLo);
 };
 
 // Drain one warp's share of an accumulator tile: TMEM lanes [32q, 32q+32) x columns [c_begin, c_end) of the
@@ -220,19 +204,24 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
           const float2 hi = __ffma2_rn(make_float2(a.z, a.w), one2, make_float2(b4.z, b4.w));
           a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
         }
-#ifdef KB_GELU_SCALAR
-        a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
-#else
         {
-          const float2 lo = gelu_erf2(make_float2(a.x, a.y)), hi = gelu_erf2(make_float2(a.z, a.w));
+          constexpr int kDeg = T::kHiLo ? 6 : 4;
+          const float2 lo = gelu_erf2<kDeg>(make_float2(a.x, a.y)), hi = gelu_erf2<kDeg>(make_float2(a.z, a.w));
           a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
         }
-#endif
         if (r >= p.M) continue;
         uint2 w;
         w.x = pack16(a.x, a.y, p.bf16);
         w.y = pack16(a.z, a.w, p.bf16);
-        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + (long long)r * p.ldo + col + tc) = w;
+        uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + (long long)r * p.ldo + col + tc;
+        *reinterpret_cast<uint2*>(orow) = w;
+        if constexpr (T::kHiLo) {  // lo = 16-bit(v - hi): hi + lo carries ~22 mantissa bits to the next split GEMM
+          const float2 h0 = unpack16(w.x, p.bf16), h1 = unpack16(w.y, p.bf16);
+          uint2 l;
+          l.x = pack16(a.x - h0.x, a.y - h0.y, p.bf16);
+          l.y = pack16(a.z - h1.x, a.w - h1.y, p.bf16);
+          *reinterpret_cast<uint2*>(orow + p.lo_off) = l;
+        }
       }
       __syncwarp();  // staging tile is rewritten by the next block
     } else {
@@ -404,22 +393,6 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
   }
 }
 
-// Residual epilogues stream 4 B/element from HBM; the read of tile i+1's residual block is started (into L2) while
-// tile i is being drained, so that the epilogue's loads hit L2 instead of paying the DRAM latency per 32x32 block.
-template <int EPI>
-__device__ __forceinline__ void prefetch_residual(const KParams& p, int lane, int row0, int col0, int ncols) {
-  if constexpr (EpiTraits<EPI>::kResid) {
-    if (!p.prefetch) return;
-    // this warp's block: 32 rows x ncols fp32 = ncols/32 lines of 128 B per row
-    const int lines_per_row = ncols >> 5;
-    for (int i = lane; i < 32 * lines_per_row; i += 32) {
-      const int r = row0 + i / lines_per_row, c = col0 + (i % lines_per_row) * 32;
-      if (r < p.M && c < p.N)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + (long long)r * p.ldr + c));
-    }
-  }
-}
-
 // ============================================================================================================
 // single-CTA tiles
 // ============================================================================================================
@@ -455,7 +428,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
-  const int num_kb = p.K / BLOCK_K;
+  const int seg_kb = p.K / BLOCK_K;  // k-blocks per pass over K
+  const int num_kb = p.nseg * seg_kb;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -488,12 +462,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1, 1);
-          mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
-          tma_load_2d(&tmap_a, &full_bar[s], smem_a + s * C::A_BYTES, kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(&tmap_b, &full_bar[s], smem_b + s * C::B_BYTES, kb * BLOCK_K, n_blk * BN);
-          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        for (int sg = 0; sg < p.nseg; ++sg) {
+          const int a0 = p.a_off[sg], w0 = p.w_off[sg];
+          for (int kb = 0; kb < seg_kb; ++kb) {
+            mbar_wait(&empty_bar[s], ph ^ 1, 1);
+            mbar_arrive_expect_tx(&full_bar[s], C::STAGE_BYTES);
+            tma_load_2d(&tmap_a, &full_bar[s], smem_a + s * C::A_BYTES, a0 + kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d(&tmap_b, &full_bar[s], smem_b + s * C::B_BYTES, w0 + kb * BLOCK_K, n_blk * BN);
+            if (++s == C::STAGES) { s = 0; ph ^= 1; }
+          }
         }
       }
     }
@@ -535,11 +512,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
-      {
-        const int nt = tile + gridDim.x;  // residual block of this warp in the CTA's next tile
-        if (nt < num_tiles)
-          prefetch_residual<EPI>(p, lane, (nt / n_tiles) * BLOCK_M + q * 32, (nt % n_tiles) * BN + half * (BN / 2), BN / 2);
-      }
       epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * BLOCK_M + q * 32, n_blk * BN, half * (BN / 2),
                          (half + 1) * (BN / 2), stage, &tfull_bar[as], aph, 4);
       // all TMEM reads of this accumulator are complete (wait::ld): hand it back to the MMA warp
@@ -560,27 +532,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // ============================================================================================================
 // CTA-pair tiles (cta_group::2): 256 x 256 output tile per cluster of two CTAs
 // ============================================================================================================
-template <int EW>  // EW = number of epilogue warps
 struct Cfg2 {
   static constexpr int BN = 256;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;    // this CTA's 128 rows of A: 16 KB
   static constexpr int B_BYTES = (BN / 2) * BLOCK_K * 2;   // this CTA's 128 rows of W: 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB per CTA per stage
-  static constexpr int STAGES = EW == 16 ? 5 : 6;
+  static constexpr int STAGES = 6;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int EPI_BYTES = EW * kStageTileBytes;
-  static constexpr int THREADS = (kFirstEpiWarp + EW) * 32;
+  static constexpr int EPI_BYTES = kNumEpiWarps * kStageTileBytes;
+  static constexpr int THREADS = kThreads;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
 };
 
-// CL = cluster size: 2 = one CTA pair per cluster; 4 = two pairs that work on vertically adjacent 256x256 tiles (same
-// columns of W): every CTA then loads only a 64-row quarter of the W tile and TMA-multicasts it to the CTA holding the
-// same half in the other pair, so L2 -> SMEM operand traffic per CTA and k-block drops from 32 KB to 24 KB.
-template <int EPI, int EW, int CL>
-__global__ void __launch_bounds__(Cfg2<EW>::THREADS, 1)
+// Variants that were measured and dropped (clusters of 4 with the W tile multicast between two pairs; mixed 4+2 clusters
+// with a dynamic scheduler; 16 epilogue warps) are described with their numbers in DESIGN.md section 8; their code is in
+// the history (commit 87a3dc2), not in the product library.
+template <int EPI>
+__global__ void __launch_bounds__(Cfg2::THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const KParams p) {
-  using C = Cfg2<EW>;
+  using C = Cfg2;
   constexpr int BN = C::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -596,18 +567,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int PAIRS = CL / 2;                  // pairs per cluster
-  const uint32_t crank = cluster_ctarank();      // rank in the cluster
-  const uint32_t rank = crank & 1;               // rank in the pair: 0 = leader (issues the MMAs)
-  const uint32_t pr = crank >> 1;                // pair index inside the cluster
-  const uint32_t leader = crank & ~1u;           // cluster rank of this pair's leader
-  const int pair = blockIdx.x / CL;              // cluster index: the unit of the persistent schedule
-  const int num_pairs = gridDim.x / CL;
-  // a cluster owns PAIRS vertically adjacent 256-row tiles ("super-tile"); the pair `pr` takes the pr-th of them
-  const int m_tiles = (p.M + PAIRS * 2 * BLOCK_M - 1) / (PAIRS * 2 * BLOCK_M);
+  const uint32_t rank = cluster_ctarank();       // rank in the pair: 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1;              // cluster index: the unit of the persistent schedule
+  const int num_pairs = gridDim.x >> 1;
+  const int m_tiles = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
-  const int num_kb = p.K / BLOCK_K;
+  const int seg_kb = p.K / BLOCK_K;              // k-blocks per pass over K
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -616,11 +582,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], PAIRS);  // a slot is multicast-written by every pair: all their MMAs must have read it
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 2 * EW);
+      mbar_init(&tempty_bar[i], 2 * kNumEpiWarps);
     }
     fence_mbar_init();
   }
@@ -640,26 +606,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       int s = 0;
       uint32_t ph = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m_blk = (tile / n_tiles) * PAIRS + (int)pr, n_blk = tile % n_tiles;
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int m0 = m_blk * 2 * BLOCK_M + rank * BLOCK_M;
         const int n0 = n_blk * BN + rank * (BN / 2);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1, 11);
-          const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[s]), leader);
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
-          tma_load_2d_cg2(&tmap_a, leader_full, smem_a + s * C::A_BYTES, kb * BLOCK_K, m0);
-          if constexpr (CL == 2) {
-            tma_load_2d_cg2(&tmap_b, leader_full, smem_b + s * C::B_BYTES, kb * BLOCK_K, n0);
-          } else {
-            // this CTA's quarter of the W tile (rows n0 + pr*QB .. +QB) goes to the CTAs of every pair that hold the
-            // same half (pair-rank `rank`): cluster ranks rank, rank + 2, ...; tmap_b has a QB-row box
-            constexpr int QB = (BN / 2) / PAIRS;
-            constexpr uint16_t kSameHalf = PAIRS == 2 ? 0b0101 : 0b01010101;
-            tma_load_2d_cg2_mc(&tmap_b, smem_u32(&full_bar[s]) & kPeerBitMask,
-                               smem_b + s * C::B_BYTES + pr * (QB * BLOCK_K * 2), kb * BLOCK_K, n0 + (int)pr * QB,
-                               (uint16_t)(kSameHalf << rank));
+        for (int sg = 0; sg < p.nseg; ++sg) {
+          const int a0 = p.a_off[sg], w0 = p.w_off[sg];
+          for (int kb = 0; kb < seg_kb; ++kb) {
+            mbar_wait(&empty_bar[s], ph ^ 1, 11);
+            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[s]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+            tma_load_2d_cg2(&tmap_a, leader_full, smem_a + s * C::A_BYTES, a0 + kb * BLOCK_K, m0);
+            tma_load_2d_cg2(&tmap_b, leader_full, smem_b + s * C::B_BYTES, w0 + kb * BLOCK_K, n0);
+            if (++s == C::STAGES) { s = 0; ph ^= 1; }
           }
-          if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -669,6 +628,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       int s = 0;
       uint32_t ph = 0;
       int lt = 0;
+      const int num_kb = p.nseg * seg_kb;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++lt) {
         const int as = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
@@ -683,249 +643,34 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
             umma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_cg2_mc(&empty_bar[s], (uint16_t)((1u << CL) - 1));  // one arrival on the slot of every CTA of the cluster
+          umma_commit_cg2_mc(&empty_bar[s], (uint16_t)0b11);  // one arrival on the slot of both CTAs
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit_cg2_mc(&tfull_bar[as], (uint16_t)(0b11u << leader));  // accumulator halves complete in both CTAs of the pair
+        umma_commit_cg2_mc(&tfull_bar[as], (uint16_t)0b11);   // accumulator halves complete in both CTAs of the pair
       }
     }
   } else if (warp >= kFirstEpiWarp) {
     // ===================== epilogue (each CTA drains its own 128 rows) =====================
     const int q = warp & 3;
-    constexpr int PARTS = EW / 4, PCOLS = BN / PARTS;  // column slices per lane quadrant
+    constexpr int PARTS = kNumEpiWarps / 4, PCOLS = BN / PARTS;  // column slices per lane quadrant
     const int part = (warp - kFirstEpiWarp) >> 2;
     uint8_t* stage = smem_epi + (warp - kFirstEpiWarp) * kStageTileBytes;
     int lt = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++lt) {
-      const int m_blk = (tile / n_tiles) * PAIRS + (int)pr, n_blk = tile % n_tiles;
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
-      {
-        const int nt = tile + num_pairs;
-        if (nt < num_tiles)
-          prefetch_residual<EPI>(p, lane, ((nt / n_tiles) * PAIRS + (int)pr) * 2 * BLOCK_M + rank * BLOCK_M + q * 32,
-                                 (nt % n_tiles) * BN + part * PCOLS, PCOLS);
-      }
       epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * 2 * BLOCK_M + rank * BLOCK_M + q * 32, n_blk * BN,
                          part * PCOLS, (part + 1) * PCOLS, stage, &tfull_bar[as], aph, 14);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[as]), leader));
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[as]), 0));
     }
   }
 
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still signal it
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
-  }
-}
-
-// ============================================================================================================
-// CTA-pair tiles on MIXED clusters: launched with a regular cluster size of 2 and a PREFERRED size of 4
-// (cudaLaunchAttributePreferredClusterDimension), so the device forms 4-CTA clusters where a GPC has room (33 on a
-// B200 = 132 SMs) and 2-CTA clusters on the SMs left over (one TPC per 9-TPC GPC). A 4-CTA cluster shares the W tile
-// between its two pairs by TMA multicast (as gemm2_kernel<.., 4>); a 2-CTA cluster is a plain pair. Because the mix is
-// only known at run time the schedule is dynamic: warp 3 of every cluster's rank-0 CTA draws 512-row "super-tiles"
-// from a global atomic counter and publishes them to all CTAs of its cluster through a small shared-memory ring
-// (st.shared::cluster + remote mbarrier arrive); a 4-CTA cluster works on both 256-row halves at once, a pair does them
-// one after the other.
-// ============================================================================================================
-constexpr int kSchedSlots = 4;
-
-template <int EPI, int EW>
-__global__ void __launch_bounds__(Cfg2<EW>::THREADS, 1)
-gemm2d_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b128,
-              const __grid_constant__ CUtensorMap tmap_b64, const KParams p, int* sched) {
-  using C = Cfg2<EW>;
-  constexpr int BN = C::BN;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
-  uint8_t* smem_epi = smem + C::STAGES * C::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + C::EPI_BYTES);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + C::STAGES;
-  uint64_t* tfull_bar = bars + 2 * C::STAGES;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* sfull_bar = tempty_bar + 2;               // [kSchedSlots] per CTA: the scheduler published a super-tile
-  uint64_t* sempty_bar = sfull_bar + kSchedSlots;     // [kSchedSlots] in the rank-0 CTA: every consumer has read it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty_bar + kSchedSlots);
-  volatile int* sched_tile = reinterpret_cast<volatile int*>(tmem_slot + 1);  // [kSchedSlots]
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t csize = cluster_nctaid_x();     // 4 (preferred) or 2 (regular)
-  const int PAIRS = (int)csize / 2;
-  const int SUBS = 2 / PAIRS;                    // 256-row halves of a super-tile this pair does one after the other
-  const uint32_t crank = cluster_ctarank();
-  const uint32_t rank = crank & 1;
-  const uint32_t pr = crank >> 1;
-  const uint32_t leader = crank & ~1u;
-  const int m_super = (p.M + 4 * BLOCK_M - 1) / (4 * BLOCK_M);
-  const int n_tiles = (p.N + BN - 1) / BN;
-  const int num_st = m_super * n_tiles;
-  const int num_kb = p.K / BLOCK_K;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(PAIRS == 2 ? &tmap_b64 : &tmap_b128);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C::STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], PAIRS);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 2 * EW);
-    }
-    for (int i = 0; i < kSchedSlots; ++i) {
-      mbar_init(&sfull_bar[i], 1);
-      // consumers of a published super-tile: per CTA the producer thread and EW epilogue warps, per pair the MMA thread
-      mbar_init(&sempty_bar[i], csize * (1 + EW) + PAIRS);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc_cg2(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish_cg2();
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // consumer side of the schedule ring: returns the next super-tile (>= num_st: no more work)
-  int sslot = 0;
-  uint32_t sph = 0;
-  auto next_super_tile = [&](bool whole_warp) {
-    mbar_wait_cluster(&sfull_bar[sslot], sph, 15);
-    const int st = sched_tile[sslot];
-    if (whole_warp) __syncwarp();
-    // Hand the slot back with a RELAXED remote arrive: a release at cluster scope would first drain this warp's global
-    // stores (the epilogue's output) - nothing is published here, the scheduler only needs to know the slot was read.
-    // The target rank is computed from `st` (always 0) so that the arrive cannot issue before the read has returned.
-    if (!whole_warp || lane == 0)
-      mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&sempty_bar[sslot]), st < 0 ? 1u : 0u));
-    if (++sslot == kSchedSlots) { sslot = 0; sph ^= 1; }
-    return st;
-  };
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int st = next_super_tile(false); st < num_st; st = next_super_tile(false)) {
-        const int n_blk = st % n_tiles;
-        const int n0 = n_blk * BN + rank * (BN / 2);
-        for (int sub = 0; sub < SUBS; ++sub) {
-          const int m_blk = (st / n_tiles) * 2 + (PAIRS == 2 ? (int)pr : sub);
-          const int m0 = m_blk * 2 * BLOCK_M + rank * BLOCK_M;
-          for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&empty_bar[s], ph ^ 1, 11);
-            const uint32_t leader_full = mapa_shared(smem_u32(&full_bar[s]), leader);
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
-            tma_load_2d_cg2(&tmap_a, leader_full, smem_a + s * C::A_BYTES, kb * BLOCK_K, m0);
-            if (PAIRS == 1) {
-              tma_load_2d_cg2(&tmap_b128, leader_full, smem_b + s * C::B_BYTES, kb * BLOCK_K, n0);
-            } else {
-              constexpr int QB = BN / 4;  // 64-row quarter of the W tile, multicast to the same half of the other pair
-              tma_load_2d_cg2_mc(&tmap_b64, smem_u32(&full_bar[s]) & kPeerBitMask,
-                                 smem_b + s * C::B_BYTES + pr * (QB * BLOCK_K * 2), kb * BLOCK_K, n0 + (int)pr * QB,
-                                 (uint16_t)(0b0101u << rank));
-            }
-            if (++s == C::STAGES) { s = 0; ph ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA of each pair) =====================
-    if (rank == 0 && lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      int lt = 0;
-      const uint16_t all_ctas = (uint16_t)((1u << csize) - 1);
-      for (int st = next_super_tile(false); st < num_st; st = next_super_tile(false)) {
-        for (int sub = 0; sub < SUBS; ++sub, ++lt) {
-          const int as = lt & 1;
-          const uint32_t aph = (lt >> 1) & 1;
-          mbar_wait(&tempty_bar[as], aph ^ 1, 12);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + as * BN;
-          for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&full_bar[s], ph, 13);
-            tc_fence_after();
-            const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + s * C::A_BYTES));
-            const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + s * C::B_BYTES));
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              umma_f16_ss_cg2(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit_cg2_mc(&empty_bar[s], all_ctas);
-            if (++s == C::STAGES) { s = 0; ph ^= 1; }
-          }
-          umma_commit_cg2_mc(&tfull_bar[as], (uint16_t)(0b11u << leader));
-        }
-      }
-    }
-  } else if (warp == 3) {
-    // ===================== scheduler (rank-0 CTA of the cluster) =====================
-    if (crank == 0 && lane == 0) {
-      int slot = 0;
-      uint32_t ph = 0;
-      while (true) {
-        mbar_wait_cluster(&sempty_bar[slot], ph ^ 1, 16);
-        // A pair needs two tile times per super-tile, a 4-CTA cluster one: near the end the pairs stop drawing, so that
-        // the last super-tiles go to the clusters that finish them in half the time (tail of one tile, not two).
-        int st;
-        if (csize == 2 && *reinterpret_cast<volatile int*>(&sched[0]) >= num_st - 2 * (int)(gridDim.x / 4)) st = num_st;
-        else st = atomicAdd(&sched[0], 1);
-        for (uint32_t c = 0; c < csize; ++c) st_shared_cluster_u32(mapa_shared(smem_u32((const void*)&sched_tile[slot]), c), (uint32_t)st);
-        for (uint32_t c = 0; c < csize; ++c) mbar_arrive_cluster(mapa_shared(smem_u32(&sfull_bar[slot]), c));  // release.cluster
-        if (st >= num_st) break;
-        if (++slot == kSchedSlots) { slot = 0; ph ^= 1; }
-      }
-      atomicAdd(&sched[csize == 4 ? 3 : 2], 1);  // statistics: clusters of each size seen so far (KEEPB200_VERBOSE)
-      // the last cluster to run dry re-arms the counters for the next launch on this stream
-      __threadfence();
-      const int done = atomicAdd(&sched[1], (int)csize) + (int)csize;
-      if (done == (int)gridDim.x) {
-        sched[0] = 0;
-        sched[1] = 0;
-        __threadfence();
-      }
-    }
-  } else if (warp >= kFirstEpiWarp) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;
-    constexpr int PARTS = EW / 4, PCOLS = BN / PARTS;
-    const int part = (warp - kFirstEpiWarp) >> 2;
-    uint8_t* stage = smem_epi + (warp - kFirstEpiWarp) * kStageTileBytes;
-    int lt = 0;
-    for (int st = next_super_tile(true); st < num_st; st = next_super_tile(true)) {
-      const int n_blk = st % n_tiles;
-      for (int sub = 0; sub < SUBS; ++sub, ++lt) {
-        const int m_blk = (st / n_tiles) * 2 + (PAIRS == 2 ? (int)pr : sub);
-        const int as = lt & 1;
-        const uint32_t aph = (lt >> 1) & 1;
-        epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * 2 * BLOCK_M + rank * BLOCK_M + q * 32, n_blk * BN,
-                           part * PCOLS, (part + 1) * PCOLS, stage, &tfull_bar[as], aph, 14);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[as]), leader));
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
@@ -945,27 +690,19 @@ KParams make_params(const GemmArgs& a, int umma_m, int umma_n) {
   p.out16 = static_cast<uint16_t*>(a.out16); p.ldo16 = a.ldo16; p.stats_out = a.stats_out;
   p.ln_stats = a.ln_stats; p.ln_s = a.ln_s; p.ln_slices = a.ln_slices;
   p.ln_inv_width = a.ln_width > 0 ? 1.0f / (float)a.ln_width : 0.f; p.ln_eps = a.ln_eps;
-  // L2 prefetch of the next tile's residual block: off. With the first residual block requested before the accumulator
-  // wait and the blocks double-buffered it no longer pays (A/B on one B200: proj 906 vs 887 TFLOP/s without it), and
-  // a K=4096 tile streams ~4 MB per CTA pair through L2 first, so the prefetched lines were evicted again (ncu: +0.4 GB
-  // of DRAM reads per fc2 launch). KEEPB200_RESID_PREFETCH=1 re-enables it for measurements.
-  static int forced = -2;
-  if (forced == -2) {
-    const char* e = std::getenv("KEEPB200_RESID_PREFETCH");
-    forced = e ? std::atoi(e) : -1;
-  }
-  p.prefetch = forced >= 0 ? forced : 0;
+  // split-operand passes: (Ah,Wh) | (Ah,Wh),(Ah,Wl) | (Ah,Wh),(Al,Wh),(Ah,Wl); the lo half sits K columns after the hi half
+  p.nseg = a.split == GEMM_SPLIT_AW ? 3 : a.split == GEMM_SPLIT_W ? 2 : 1;
+  for (int i = 0; i < 3; ++i) p.a_off[i] = p.w_off[i] = 0;
+  if (a.split == GEMM_SPLIT_AW) { p.a_off[1] = a.K; p.w_off[2] = a.K; }
+  if (a.split == GEMM_SPLIT_W) p.w_off[1] = a.K;
+  p.lo_off = a.lo_off;
   return p;
 }
 
 template <int BN, int EPI>
 int launch_one(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   using C = Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    KB_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
+  KB_TRY_ATTR((gemm_kernel<BN, EPI>), C::SMEM_BYTES);
   const KParams p = make_params(a, BLOCK_M, BN);
   const int tiles = ((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BN - 1) / BN);
   int grid = num_sms();
@@ -979,117 +716,30 @@ int launch_one(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, 
   return KB_OK;
 }
 
-// CTAs per cluster of the pair kernel. 4 = the W tile is shared by two pairs through TMA multicast: +8-10 % throughput
-// per SM, but only 33 clusters of 4 are co-resident on a B200 (132 of 148 SMs: one TPC per 9-TPC GPC is left over), so
-// the whole GEMM is 1-3 % slower than with pairs (A/B in the step: 7,152 vs 7,230 tiles/s). Default 2;
-// KEEPB200_GEMM_CLUSTER=4 selects the multicast variant (read per call: tests exercise both in one process).
-int pair_cluster_size() {
-  const char* e = std::getenv("KEEPB200_GEMM_CLUSTER");
-  if (e && !std::strcmp(e, "mixed")) return 6;  // 4-CTA clusters where they fit + pairs on the rest, dynamic schedule
-  return (e && std::atoi(e) == 4) ? 4 : 2;
-}
-
-template <int EPI, int EW, int CL>
-int launch_pair_ew(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
-  using C = Cfg2<EW>;
-  static int max_clusters = 0;  // clusters of CL CTAs (one per SM, 227 KB of shared memory each) that can be co-resident
-  if (max_clusters == 0) {
-    KB_CUDA_CHECK(cudaFuncSetAttribute(gemm2_kernel<EPI, EW, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    cudaLaunchConfig_t q = {};
-    q.gridDim = dim3((unsigned)(num_sms() / CL * CL));
-    q.blockDim = dim3(C::THREADS);
-    q.dynamicSmemBytes = C::SMEM_BYTES;
-    cudaLaunchAttribute at;
-    at.id = cudaLaunchAttributeClusterDimension;
-    at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
-    q.attrs = &at; q.numAttrs = 1;
-    int n = 0;
-    KB_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<EPI, EW, CL>, &q));
-    if (n <= 0) return set_error(KB_ERR_CUDA, "gemm: no cluster of %d CTAs fits on this device", CL);
-    max_clusters = n;
-    if (std::getenv("KEEPB200_VERBOSE")) fprintf(stderr, "keep_b200: gemm2<epi %d> clusters of %d: %d co-resident (%d SMs)\n", EPI, CL, n, n * CL);
-  }
+template <int EPI>
+int launch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+  using C = Cfg2;
+  KB_TRY_ATTR((gemm2_kernel<EPI>), C::SMEM_BYTES);
   const KParams p = make_params(a, 2 * BLOCK_M, C::BN);
-  constexpr int PAIRS = CL / 2;
-  const int tiles = ((a.M + PAIRS * 2 * BLOCK_M - 1) / (PAIRS * 2 * BLOCK_M)) * ((a.N + C::BN - 1) / C::BN);
-  int clusters = num_sms() / CL;
-  if (max_clusters < clusters) clusters = max_clusters;
+  const int tiles = ((a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((a.N + C::BN - 1) / C::BN);
+  int clusters = num_sms() / 2;  // one CTA per SM (227 KB of shared memory each); 148 SMs = 74 pairs, all co-resident
   if (tiles < clusters) clusters = tiles;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(CL * clusters));
+  cfg.gridDim = dim3((unsigned)(2 * clusters));
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute at;
   at.id = cudaLaunchAttributeClusterDimension;
-  at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
   cfg.attrs = &at; cfg.numAttrs = 1;
   profile_gemm_tag(a.M, a.N, a.K, a.epi);
   profile_gemm_begin(stream);
-  KB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm2_kernel<EPI, EW, CL>, ta, tb, p));
+  KB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm2_kernel<EPI>, ta, tb, p));
   profile_gemm_end(stream, 2.0 * a.M * a.N * a.K);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
-}
-
-// one {next, done} counter pair per stream (device memory, zero at rest: the kernel re-arms it)
-int* sched_counters(cudaStream_t stream) {
-  static std::mutex mu;
-  static std::map<cudaStream_t, int*> bufs;
-  std::lock_guard<std::mutex> g(mu);
-  auto it = bufs.find(stream);
-  if (it != bufs.end()) return it->second;
-  int* p = nullptr;
-  if (cudaMalloc(&p, 4 * sizeof(int)) != cudaSuccess) return nullptr;  // next, done, #pair clusters, #quad clusters
-  cudaMemset(p, 0, 4 * sizeof(int));
-  bufs[stream] = p;
-  return p;
-}
-
-template <int EPI, int EW>
-int launch_pair_dynamic(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb128, const CUtensorMap& tb64,
-                        cudaStream_t stream) {
-  using C = Cfg2<EW>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    KB_CUDA_CHECK(cudaFuncSetAttribute(gemm2d_kernel<EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    KB_CUDA_CHECK(cudaFuncSetAttribute(gemm2d_kernel<EPI, EW>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    attr_set = true;
-  }
-  int* sched = sched_counters(stream);
-  if (sched == nullptr) return set_error(KB_ERR_CUDA, "gemm: cannot allocate the tile-scheduler counters");
-  const KParams p = make_params(a, 2 * BLOCK_M, C::BN);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(num_sms() / 4 * 4));  // every SM; a multiple of the preferred cluster size
-  cfg.blockDim = dim3(C::THREADS);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute at[2];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  at[1].id = cudaLaunchAttributePreferredClusterDimension;
-  at[1].val.preferredClusterDim.x = 4; at[1].val.preferredClusterDim.y = 1; at[1].val.preferredClusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 2;
-  profile_gemm_tag(a.M, a.N, a.K, a.epi);
-  profile_gemm_begin(stream);
-  KB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm2d_kernel<EPI, EW>, ta, tb128, tb64, p, sched));
-  profile_gemm_end(stream, 2.0 * a.M * a.N * a.K);
-  if (std::getenv("KEEPB200_VERBOSE")) {
-    int h[4] = {0, 0, 0, 0};
-    cudaStreamSynchronize(stream);
-    cudaMemcpy(h, sched, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "keep_b200: gemm2d<epi %d>: clusters so far: %d of 2 CTAs, %d of 4 CTAs\n", EPI, h[2], h[3]);
-  }
-  note_launch();
-  KB_CUDA_CHECK(cudaGetLastError());
-  return KB_OK;
-}
-
-template <int EPI>
-int launch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
-  // 8 epilogue warps: a 16-warp variant (102 registers/thread) was measured no faster on fc1 and slower on proj
-  return a.cluster == 4 ? launch_pair_ew<EPI, 8, 4>(a, ta, tb, stream) : launch_pair_ew<EPI, 8, 2>(a, ta, tb, stream);
 }
 
 #define KB_DISPATCH_EPI(FN, ...)                                                             \
@@ -1102,40 +752,15 @@ int launch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb,
     case EPI_RESID_F32_STATS: return FN<__VA_ARGS__ EPI_RESID_F32_STATS>(a, ta, tb, stream); \
     case EPI_LN_BIAS_HALF: return FN<__VA_ARGS__ EPI_LN_BIAS_HALF>(a, ta, tb, stream);       \
     case EPI_LN_BIAS_GELU_HALF: return FN<__VA_ARGS__ EPI_LN_BIAS_GELU_HALF>(a, ta, tb, stream); \
+    case EPI_BIAS_GELU_HILO: return FN<__VA_ARGS__ EPI_BIAS_GELU_HILO>(a, ta, tb, stream);   \
     default: return set_error(KB_ERR_ARG, "gemm: unknown epilogue %d", a.epi);               \
   }
 
-int dispatch_256(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
-  KB_DISPATCH_EPI(launch_one, 256, )
-}
 int dispatch_128(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   KB_DISPATCH_EPI(launch_one, 128, )
 }
 int dispatch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   KB_DISPATCH_EPI(launch_pair, )
-}
-template <int EPI>
-int launch_pair_dyn8(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
-  CUtensorMap tb64;
-  int rc = get_tmap_2d(a.W, a.bf16 ? KB_BF16 : KB_F16, a.N, a.K, a.ldw, 64, &tb64);
-  if (rc) return rc;
-  return launch_pair_dynamic<EPI, 8>(a, ta, tb, tb64, stream);
-}
-int dispatch_pair_dynamic(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
-  KB_DISPATCH_EPI(launch_pair_dyn8, )
-}
-
-// KEEPB200_GEMM = auto (default) | pair | wide | narrow : force one main-loop variant (A/B measurements)
-int forced_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = std::getenv("KEEPB200_GEMM");
-    mode = 0;
-    if (e && !std::strcmp(e, "pair")) mode = 1;
-    if (e && !std::strcmp(e, "wide")) mode = 2;
-    if (e && !std::strcmp(e, "narrow")) mode = 3;
-  }
-  return mode;
 }
 
 }  // namespace
@@ -1153,29 +778,24 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     return set_error(KB_ERR_ARG, "gemm: LayerNorm epilogue needs ln_stats, ln_s, an even ln_slices and ln_width");
   if (a.epi == EPI_PATCH_F32 && (a.pos == nullptr || a.patches <= 0))
     return set_error(KB_ERR_ARG, "gemm: patch epilogue without pos/patches");
-  // Variant choice: CTA-pair 256x256 tiles when they fill the machine; otherwise 128-row tiles, 256 wide when
-  // that still gives every SM a tile, else 128 wide (twice as many work units for small problems).
-  const long long m128 = (a.M + BLOCK_M - 1) / BLOCK_M, m256 = (a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-  const bool n256 = (a.N % 256 == 0);
-  int mode = forced_mode();
-  if (mode == 0) mode = (n256 && m256 * (a.N / 256) >= num_sms() / 2) ? 1 : (n256 && m128 * (a.N / 256) >= num_sms()) ? 2 : 3;
-  if ((mode == 1 || mode == 2) && !n256) mode = 3;
+  if (a.split != GEMM_SPLIT_NONE && a.split != GEMM_SPLIT_W && a.split != GEMM_SPLIT_AW)
+    return set_error(KB_ERR_ARG, "gemm: unknown split mode %d", a.split);
+  if (a.epi == EPI_BIAS_GELU_HILO && a.lo_off <= 0) return set_error(KB_ERR_ARG, "gemm: hi|lo epilogue without lo_off");
+  // Variant choice (a function of the shape only: the same problem always runs the same kernel): CTA-pair 256x256
+  // tiles when they give every pair of SMs a tile; otherwise single-CTA 128x128 tiles (four times as many work units
+  // for the small problems: CLS-row tails, small batches, the text tower of a WSI prompt set).
+  const long long m256 = (a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const bool pair = (a.N % 256 == 0) && m256 * (a.N / 256) >= num_sms() / 2;
   const int dt = a.bf16 ? KB_BF16 : KB_F16;
+  // a split operand is a [rows, 2K] hi|lo matrix (row pitch >= 2K): the maps span both halves
+  const int64_t a_cols = a.split == GEMM_SPLIT_AW ? 2LL * a.K : a.K, w_cols = a.split != GEMM_SPLIT_NONE ? 2LL * a.K : a.K;
+  if (a.lda < a_cols || a.ldw < w_cols) return set_error(KB_ERR_ARG, "gemm: row pitch smaller than the (split) operand width");
   CUtensorMap ta, tb;
-  int rc = get_tmap_2d(a.A, dt, a.M, a.K, a.lda, BLOCK_M, &ta);
+  int rc = get_tmap_2d(a.A, dt, a.M, a_cols, a.lda, BLOCK_M, &ta);
   if (rc) return rc;
-  // pair kernel: clusters of 4 (W tile multicast between two pairs) when there are enough 512-row super-tiles
-  GemmArgs a2 = a;
-  const bool many = ((a.M + 511) / 512) * (a.N / 256) >= num_sms() / 4;
-  a2.cluster = (mode == 1 && pair_cluster_size() == 4 && many) ? 4 : 2;
-  if (mode == 1 && pair_cluster_size() == 6 && many) {
-    rc = get_tmap_2d(a.W, dt, a.N, a.K, a.ldw, 128, &tb);
-    if (rc) return rc;
-    return dispatch_pair_dynamic(a2, ta, tb, stream);
-  }
-  rc = get_tmap_2d(a.W, dt, a.N, a.K, a.ldw, mode == 2 ? 256 : (mode == 1 && a2.cluster == 4) ? 64 : 128, &tb);
+  rc = get_tmap_2d(a.W, dt, a.N, w_cols, a.ldw, 128, &tb);
   if (rc) return rc;
-  return mode == 1 ? dispatch_pair(a2, ta, tb, stream) : mode == 2 ? dispatch_256(a, ta, tb, stream) : dispatch_128(a, ta, tb, stream);
+  return pair ? dispatch_pair(a, ta, tb, stream) : dispatch_128(a, ta, tb, stream);
 }
 
 }  // namespace kb

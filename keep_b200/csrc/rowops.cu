@@ -30,13 +30,25 @@ __device__ __forceinline__ uint2 pack4(float4 v, int bf16) {
   }
   return r;
 }
+// rounding remainder of pack4: lo = 16-bit(v - hi)
+__device__ __forceinline__ uint2 pack4_lo(float4 v, uint2 hi, int bf16) {
+  float4 h;
+  if (bf16) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&hi.x)), b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&hi.y));
+    h = make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    const float2 a = __half22float2(*reinterpret_cast<__half2*>(&hi.x)), b = __half22float2(*reinterpret_cast<__half2*>(&hi.y));
+    h = make_float4(a.x, a.y, b.x, b.y);
+  }
+  return pack4(make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w), bf16);
+}
 
 // NV = D / 128 float4 per lane
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, long long row_stride,
                                                         long long rows, const float* __restrict__ w,
                                                         const float* __restrict__ b, float eps, uint16_t* y16, int bf16,
-                                                        float* y32) {
+                                                        float* y32, long long y16_pitch, long long lo_off) {
   constexpr int D = NV * 128;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -66,7 +78,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* x, long lon
     o.y = v[i].y * rstd * ww.y + bb.y;
     o.z = v[i].z * rstd * ww.z + bb.z;
     o.w = v[i].w * rstd * ww.w + bb.w;
-    if (y16) *reinterpret_cast<uint2*>(y16 + row * D + (lane + 32 * i) * 4) = pack4(o, bf16);
+    if (y16) {
+      const uint2 hi = pack4(o, bf16);
+      *reinterpret_cast<uint2*>(y16 + row * y16_pitch + (lane + 32 * i) * 4) = hi;
+      if (lo_off > 0) *reinterpret_cast<uint2*>(y16 + row * y16_pitch + lo_off + (lane + 32 * i) * 4) = pack4_lo(o, hi, bf16);
+    }
     if (y32) *reinterpret_cast<float4*>(y32 + row * D + (lane + 32 * i) * 4) = o;
   }
 }
@@ -92,6 +108,21 @@ __global__ void __launch_bounds__(256) act_l2norm_kernel(const float* __restrict
   for (int i = 0; i < NV; ++i) {
     float4 o = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
     *reinterpret_cast<float4*>(y + row * D + (lane + 32 * i) * 4) = o;
+  }
+}
+
+// dst[r, 0:K] = 16-bit(src[r, :]), dst[r, K:2K] = 16-bit(src - hi): the [rows, 2K] hi|lo operand of a split GEMM
+__global__ void cast_hilo_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, long long rows, int K4, int bf16) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x, n4 = rows * K4;
+  for (; i < n4; i += stride) {
+    const long long r = i / K4;
+    const int c = (int)(i % K4);
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const uint2 hi = pack4(v, bf16);
+    uint2* drow = reinterpret_cast<uint2*>(dst + r * (8LL * K4));
+    drow[c] = hi;
+    drow[K4 + c] = pack4_lo(v, hi, bf16);
   }
 }
 
@@ -171,12 +202,15 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
   }
 
 int launch_layernorm(const float* x, int64_t x_row_stride, int64_t rows, int D, const float* w, const float* b,
-                     float eps, void* y16, int bf16, float* y32, cudaStream_t stream) {
+                     float eps, void* y16, int bf16, float* y32, cudaStream_t stream, int64_t y16_pitch, int64_t lo_off) {
   if (rows <= 0) return KB_OK;
   if (D % 128 != 0 || x_row_stride % 4 != 0) return set_error(KB_ERR_ARG, "layernorm: D=%d / stride not vectorisable", D);
+  if (y16_pitch <= 0) y16_pitch = D;
+  if (y16_pitch % 4 != 0 || lo_off % 4 != 0 || (lo_off > 0 && lo_off + D > y16_pitch))
+    return set_error(KB_ERR_ARG, "layernorm: 16-bit output pitch %lld / lo offset %lld invalid for D=%d", (long long)y16_pitch, (long long)lo_off, D);
   const unsigned grid = (unsigned)((rows + 7) / 8);
   KB_DISPATCH_NV(D / 128, (layernorm_kernel<NV><<<grid, 256, 0, stream>>>(x, x_row_stride, rows, w, b, eps,
-                                                                          (uint16_t*)y16, bf16, y32)));
+                                                                          (uint16_t*)y16, bf16, y32, y16_pitch, lo_off)));
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
@@ -199,6 +233,18 @@ int launch_cast_f32_to_16(const float* src, void* dst, int64_t n, int bf16, cuda
   unsigned grid = (unsigned)((n4 + 255) / 256);
   if (grid > (unsigned)num_sms() * 16) grid = num_sms() * 16;
   cast_kernel<<<grid, 256, 0, stream>>>(src, (uint16_t*)dst, n4, bf16);
+  note_launch();
+  KB_CUDA_CHECK(cudaGetLastError());
+  return KB_OK;
+}
+
+int launch_cast_f32_to_hilo(const float* src, void* dst, int64_t rows, int K, int bf16, cudaStream_t stream) {
+  if (rows <= 0 || K <= 0) return KB_OK;
+  if (K % 4 != 0) return set_error(KB_ERR_ARG, "cast hi|lo: K=%d must be a multiple of 4", K);
+  const long long n4 = rows * (K / 4);
+  unsigned grid = (unsigned)((n4 + 255) / 256);
+  if (grid > (unsigned)num_sms() * 16) grid = num_sms() * 16;
+  cast_hilo_kernel<<<grid, 256, 0, stream>>>(src, (uint16_t*)dst, rows, K / 4, bf16);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;

@@ -26,18 +26,17 @@ int set_error(int code, const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
-int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+int num_sms() {  // of the CURRENT device (a process may drive several GPUs: cached per device index)
+  static int cache[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-    // KEEPB200_SMS=<k>: size the persistent grids for k SMs (experiments with kernels of two streams side by side)
-    const char* e = std::getenv("KEEPB200_SMS");
-    if (e && std::atoi(e) >= 2 && std::atoi(e) <= n) n = std::atoi(e) & ~1;
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
 }
 
 // ---------------------------------------------------------------------------------------------------

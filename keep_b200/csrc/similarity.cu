@@ -10,8 +10,6 @@
 #include "common.h"
 #include "ptx.cuh"
 
-#include <cstdlib>
-#include <cstring>
 
 namespace kb {
 namespace {
@@ -96,9 +94,10 @@ __global__ void group_softmax_kernel(const float* __restrict__ logits, long long
   for (int j = 0; j < group; ++j) dst[j] = expf(src[j] * temp - mx) * inv;
 }
 
-// one thread per (row, classifier); block partial sums -> one atomicAdd per classifier per block
+// one thread per (row, classifier); every block of 256 rows writes its partial sums to its own row of `part`
+// ([gridDim.y, K]): no atomics, so the reduction order - and with it the ranking of near-tied classifiers - is fixed
 __global__ void __launch_bounds__(256)
-prompt_score_kernel(const float* __restrict__ logits, long long rows, int K, int C, float* __restrict__ scores) {
+prompt_score_kernel(const float* __restrict__ logits, long long rows, int K, int C, float* __restrict__ parts) {
   // grid: x over classifiers (blocks of 32), y over row blocks of 256; thread layout 32 (k) x 8 (rows)
   const int k = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ry = threadIdx.x >> 5;
@@ -121,13 +120,8 @@ prompt_score_kernel(const float* __restrict__ logits, long long rows, int K, int
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x & 31];
-    atomicAdd(scores + k, s);
+    parts[(long long)blockIdx.y * K + k] = s;
   }
-}
-
-__global__ void scale_kernel(float* v, long long n, float s) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) v[i] *= s;
 }
 
 }  // namespace
@@ -139,12 +133,7 @@ int launch_similarity(const float* feats, int64_t N, int D, const float* cls, in
   if (logits == nullptr) return set_error(KB_ERR_ARG, "similarity: logits buffer is required");
   if (group <= 0) group = P;
   if (P % group != 0) return set_error(KB_ERR_ARG, "similarity: P=%d is not a multiple of group=%d", P, group);
-  static int force_fma = -1;
-  if (force_fma < 0) {
-    const char* e = std::getenv("KEEPB200_SIM");
-    force_fma = (e && !std::strcmp(e, "fma")) ? 1 : 0;
-  }
-  if (clsT_scratch != nullptr && D % 32 == 0 && !force_fma && (reinterpret_cast<uintptr_t>(feats) & 15) == 0) {
+  if (clsT_scratch != nullptr && D % 32 == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0) {
     // tensor-core path: classifier transposed to K-major [P, D] (tiny), TF32 tcgen05 GEMM with fused epilogue
     int rc = launch_transpose_f32(cls, clsT_scratch, D, P, stream);
     if (rc) return rc;
@@ -210,19 +199,19 @@ int launch_prompt_scores_fused(const float* feats, int64_t N, int D, const float
   return KB_OK;
 }
 
-int launch_prompt_score_accum(const float* logits, int64_t rows, int K, int C, float* scores, cudaStream_t stream) {
+int launch_prompt_score_partials(const float* logits, int64_t rows, int K, int C, float* part, cudaStream_t stream) {
   if (rows <= 0 || K <= 0) return KB_OK;
   if (C < 2) return set_error(KB_ERR_ARG, "prompt scores: need at least 2 classes per classifier (got %d)", C);
   dim3 grid((unsigned)((K + 31) / 32), (unsigned)((rows + 255) / 256));
-  prompt_score_kernel<<<grid, 256, 0, stream>>>(logits, rows, K, C, scores);
+  prompt_score_kernel<<<grid, 256, 0, stream>>>(logits, rows, K, C, part);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }
 
-int launch_scale(float* v, int64_t n, float s, cudaStream_t stream) {
-  if (n <= 0) return KB_OK;
-  scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(v, n, s);
+int launch_score_reduce(const float* part, int64_t nparts, int K, float scale, float* scores, cudaStream_t stream) {
+  if (K <= 0) return KB_OK;
+  score_reduce_kernel<<<(unsigned)((K + 127) / 128), 128, 0, stream>>>(part, nparts, K, scale, scores);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;

@@ -308,11 +308,7 @@ int launch_similarity_tc(const float* feats, int64_t N, int D, const float* clsT
   rc = get_tmap_2d(clsT, KB_F32, P, D, D, BN, &tb);
   if (rc) return rc;
   const int smem = stages * (A_BYTES + b_bytes) + 2 * SBM * 4 + 512 + 1024;
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    KB_CUDA_CHECK(cudaFuncSetAttribute(sim_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    smem_set = smem;
-  }
+  KB_TRY_ATTR(sim_tc_kernel, smem);
   SimParams p;
   p.N = N; p.D = D; p.P = P; p.BN = BN; p.stages = stages; p.group = group; p.temp = temp;
   p.logits = logits; p.probs = probs; p.score_part = score_part;

@@ -67,6 +67,10 @@ def to_device(t: torch.Tensor, device, chunk_rows: int = 16384) -> torch.Tensor:
     stage = [torch.empty((rows,) + tuple(t.shape[1:]), dtype=t.dtype, pin_memory=True) for _ in range(2)]
     done = [torch.cuda.Event() for _ in range(2)]
     copy_stream = torch.cuda.Stream(device)
+    # `out` was allocated on the current stream: the caching allocator may have handed back a block that kernels already
+    # queued on that stream still read (the previous slide's features), so the copies must be ordered after them
+    copy_stream.wait_stream(torch.cuda.current_stream(device))
+    out.record_stream(copy_stream)
     for i, r0 in enumerate(range(0, n, rows)):
         k = min(rows, n - r0)
         s = i & 1

@@ -149,7 +149,8 @@ class KEEPModel(PreTrainedModel):
         self._dirty = False
 
     def _workspace(self, nbytes: int, dev) -> torch.Tensor:
-        if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:
+        # + 1024: _aligned() may move the base up by as much as 1023 bytes
+        if self._ws is None or self._ws.numel() < nbytes + 1024 or self._ws.device != dev:
             self._ws = None
             self._ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
         return self._ws
@@ -219,35 +220,88 @@ class KEEPModel(PreTrainedModel):
         tt = text_inputs.get("token_type_ids")
         mask = text_inputs.get("attention_mask")
         tt = tt.to(device=dev, dtype=torch.long).contiguous() if tt is not None else None
-        hidden = self.config.text()["hidden_size"]
+        tcfg = self.config.text()
+        hidden = tcfg["hidden_size"]
         out = torch.empty(P, hidden, dtype=torch.float32, device=dev)
         if P == 0:
             return out
+        precision = {"auto": _lib.TEXT_AUTO, "high": _lib.TEXT_HIGH, "fast": _lib.TEXT_FAST}.get(
+            str(getattr(self.config, "text_precision", "auto")))
+        if precision is None:
+            raise ValueError(f"text_precision must be 'auto', 'high' or 'fast', got {self.config.text_precision!r}")
         s_eff = S
         if mask is not None:
             mask = mask.to(device=dev, dtype=torch.long).contiguous()
+        # One device->host read for all the facts the host needs. Out-of-range ids raise as nn.Embedding would (the
+        # kernel clamps only to stay memory-safe). A row that attends to nothing is refused: BertModel would add
+        # finfo.min to every score of that row and average V over all positions, pads included - no tokenizer
+        # produces such a row, and silently returning something else is not an option here.
+        facts = [ids.min(), ids.max(), tt.min() if tt is not None else ids.new_zeros(()),
+                 tt.max() if tt is not None else ids.new_zeros(())]
         if mask is not None:
-            # One device->host read for both facts. A row that attends to nothing is refused: BertModel would add
-            # finfo.min to every score of that row and average V over all positions, pads included - no tokenizer
-            # produces such a row, and silently returning something else is not an option here.
             attended = mask != 0
-            facts = torch.stack([attended.any(dim=1).all().to(torch.long),
-                                 (attended.any(dim=0).to(torch.long) * torch.arange(1, S + 1, device=dev)).max()]).tolist()
-            if not facts[0]:
+            facts += [attended.any(dim=1).all().to(torch.long),
+                      (attended.any(dim=0).to(torch.long) * torch.arange(1, S + 1, device=dev)).max()]
+        facts = torch.stack(facts).tolist()
+        if facts[0] < 0 or facts[1] >= tcfg["vocab_size"]:
+            raise IndexError(f"encode_text: input_ids outside [0, {tcfg['vocab_size']}) (min {facts[0]}, max {facts[1]})")
+        if facts[2] < 0 or facts[3] >= tcfg["type_vocab_size"]:
+            raise IndexError(f"encode_text: token_type_ids outside [0, {tcfg['type_vocab_size']})")
+        if mask is not None:
+            if not facts[4]:
                 raise ValueError("encode_text: an attention_mask row has no attended position")
             if self.trim_text:
                 # positions past the last attended key in EVERY row contribute exactly zero to the [CLS] output
-                s_eff = max(int(facts[1]), 1)
+                s_eff = max(int(facts[5]), 1)
         L = _lib.lib()
         with torch.cuda.device(dev):
             chunk = max(1, min(P, self.text_chunk_tokens // s_eff))
             need = L.keepb200_workspace_bytes(self._handle, OP_ENCODE_TEXT, chunk, s_eff)
             ws = self._workspace(need, dev)
             _lib.check(
-                L.keepb200_encode_text(self._handle, ids.data_ptr(), _lib.ptr(tt), _lib.ptr(mask), P, S, s_eff,
+                L.keepb200_encode_text(self._handle, ids.data_ptr(), _lib.ptr(tt), _lib.ptr(mask), P, S, s_eff, precision,
                                        out.data_ptr(), self._aligned(ws), need, _lib.stream_ptr(dev)),
                 "encode_text")
         return out
+
+    # ---- test / analysis hooks (include/keep_b200.h "debug") -----------------------------------------------------
+    def debug_set_ln_fuse(self, mode: int) -> None:
+        """LayerNorm placement in the ViT blocks (0 stand-alone, 1 default, 2 norm2 folded as well)."""
+        self._sync()
+        _lib.check(_lib.lib().keepb200_debug_set_ln_fuse(self._handle, int(mode)), "debug_set_ln_fuse")
+
+    @torch.no_grad()
+    def debug_layer_outputs(self, image_inputs=None, text_inputs=None):
+        """Residual stream after every block of ONE tower for a small batch: list of [B, T, D] tensors (the last entry
+        holds the CLS rows only, [B, D]) - what the per-layer parity table compares with hooks on the oracle."""
+        self._sync()
+        dev = self._device()
+        L = _lib.lib()
+        if (image_inputs is None) == (text_inputs is None):
+            raise ValueError("give exactly one of image_inputs / text_inputs")
+        if image_inputs is not None:
+            v = self.config.vision()
+            B = image_inputs.shape[0]
+            T = (image_inputs.shape[-2] // 16) * (image_inputs.shape[-1] // 16) + 1
+            depth, D = v["depth"], v["width"]
+            if B > self.image_chunk:
+                raise ValueError("debug_layer_outputs: the batch must fit one workspace chunk")
+        else:
+            t = self.config.text()
+            depth, D = t["num_hidden_layers"], t["hidden_size"]
+            B = text_inputs["input_ids"].shape[0]
+            m = text_inputs.get("attention_mask")
+            T = text_inputs["input_ids"].shape[1] if (m is None or not self.trim_text) else \
+                max(int(((m != 0).any(dim=0).long() * torch.arange(1, m.shape[1] + 1, device=m.device)).max()), 1)
+        buf = torch.zeros(depth, B * T * D, dtype=torch.float32, device=dev)
+        _lib.check(L.keepb200_debug_layer_dump(self._handle, buf.data_ptr(), buf.numel() * 4), "debug_layer_dump")
+        try:
+            final = self.encode_image(image_inputs) if image_inputs is not None else self.encode_text(text_inputs)
+            torch.cuda.synchronize(dev)
+        finally:
+            _lib.check(L.keepb200_debug_layer_dump(self._handle, None, 0), "debug_layer_dump")
+        outs = [buf[i].view(B, T, D) for i in range(depth - 1)] + [buf[depth - 1, :B * D].view(B, D)]
+        return outs, final
 
     def forward(self, image_inputs, text_inputs):
         """keep_inference.py:65-73."""

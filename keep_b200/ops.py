@@ -9,6 +9,14 @@ import torch
 from . import _lib
 
 EPI_BIAS_HALF, EPI_BIAS_GELU_HALF, EPI_RESID_F32, EPI_BIAS_F32, EPI_PATCH_F32 = range(5)
+EPI_BIAS_GELU_HILO = 8
+SPLIT_NONE, SPLIT_W, SPLIT_AW = 0, 1, 2
+
+
+def _on(t):
+    """Make the tensor's device current for the call: the library sizes its grids and caches kernel attributes per
+    CURRENT device, so a process that drives several GPUs must launch with the right one selected."""
+    return torch.cuda.device(t.device)
 
 
 def _need_cuda(*ts):
@@ -41,14 +49,15 @@ def gemm(a, w, epi, bias=None, gamma=None, resid=None, out=None, pos=None, patch
         else:
             out = torch.empty(M, N, dtype=torch.float32, device=a.device)
     L = _lib.lib()
-    _lib.check(
-        L.keepb200_op_gemm(
-            a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, epi, bf,
-            _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(resid), resid.stride(0) if resid is not None else 0,
-            out.data_ptr(), out.stride(0), _lib.ptr(pos), patches, _lib.stream_ptr(a.device),
-        ),
-        "op_gemm",
-    )
+    with _on(a):
+        _lib.check(
+            L.keepb200_op_gemm(
+                a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, epi, bf,
+                _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(resid), resid.stride(0) if resid is not None else 0,
+                out.data_ptr(), out.stride(0), _lib.ptr(pos), patches, _lib.stream_ptr(a.device),
+            ),
+            "op_gemm",
+        )
     return out
 
 
@@ -61,11 +70,12 @@ def gemm_resid_stats(a, w, x, bias=None, gamma=None):
     x16 = torch.empty(M, N, dtype=a.dtype, device=a.device)
     stats = torch.zeros(M, N // 64, 2, dtype=torch.float32, device=a.device)
     L = _lib.lib()
-    _lib.check(
-        L.keepb200_op_gemm_resid_stats(a.data_ptr(), w.data_ptr(), M, N, K, _is_bf16(a), _lib.ptr(bias), _lib.ptr(gamma),
-                                       x.data_ptr(), x16.data_ptr(), stats.data_ptr(), _lib.stream_ptr(a.device)),
-        "op_gemm_resid_stats",
-    )
+    with _on(a):
+        _lib.check(
+            L.keepb200_op_gemm_resid_stats(a.data_ptr(), w.data_ptr(), M, N, K, _is_bf16(a), _lib.ptr(bias), _lib.ptr(gamma),
+                                           x.data_ptr(), x16.data_ptr(), stats.data_ptr(), _lib.stream_ptr(a.device)),
+            "op_gemm_resid_stats",
+        )
     return x16, stats
 
 
@@ -77,11 +87,12 @@ def fold_ln(w32, lnw, lnb, bias, dtype=torch.float16):
     s = torch.empty(N, dtype=torch.float32, device=w32.device)
     c = torch.empty(N, dtype=torch.float32, device=w32.device)
     L = _lib.lib()
-    _lib.check(
-        L.keepb200_op_fold_ln(w32.data_ptr(), N, K, lnw.data_ptr(), lnb.data_ptr(), _lib.ptr(bias), w16.data_ptr(),
-                              1 if dtype == torch.bfloat16 else 0, s.data_ptr(), c.data_ptr(), _lib.stream_ptr(w32.device)),
-        "op_fold_ln",
-    )
+    with _on(w32):
+        _lib.check(
+            L.keepb200_op_fold_ln(w32.data_ptr(), N, K, lnw.data_ptr(), lnb.data_ptr(), _lib.ptr(bias), w16.data_ptr(),
+                                  1 if dtype == torch.bfloat16 else 0, s.data_ptr(), c.data_ptr(), _lib.stream_ptr(w32.device)),
+            "op_fold_ln",
+        )
     return w16, s, c
 
 
@@ -92,11 +103,12 @@ def gemm_ln(x16, wf, s, c, stats, eps, gelu=False):
     N = wf.shape[0]
     out = torch.empty(M, N, dtype=x16.dtype, device=x16.device)
     L = _lib.lib()
-    _lib.check(
-        L.keepb200_op_gemm_ln(x16.data_ptr(), wf.data_ptr(), M, N, K, 1 if gelu else 0, _is_bf16(x16), c.data_ptr(),
-                              s.data_ptr(), stats.data_ptr(), eps, out.data_ptr(), _lib.stream_ptr(x16.device)),
-        "op_gemm_ln",
-    )
+    with _on(x16):
+        _lib.check(
+            L.keepb200_op_gemm_ln(x16.data_ptr(), wf.data_ptr(), M, N, K, 1 if gelu else 0, _is_bf16(x16), c.data_ptr(),
+                                  s.data_ptr(), stats.data_ptr(), eps, out.data_ptr(), _lib.stream_ptr(x16.device)),
+            "op_gemm_ln",
+        )
     return out
 
 
@@ -107,42 +119,110 @@ def pos_resample(pos, g0, gh, gw):
     pos = pos.reshape(1 + g0 * g0, D).contiguous()
     out = torch.empty(1 + gh * gw, D, dtype=torch.float32, device=pos.device)
     L = _lib.lib()
-    _lib.check(L.keepb200_op_pos_resample(pos.data_ptr(), g0, gh, gw, D, out.data_ptr(), _lib.stream_ptr(pos.device)),
-               "op_pos_resample")
+    with _on(pos):
+        _lib.check(L.keepb200_op_pos_resample(pos.data_ptr(), g0, gh, gw, D, out.data_ptr(), _lib.stream_ptr(pos.device)),
+                   "op_pos_resample")
     return out
 
 
-def layernorm(x, w, b, eps, out_dtype=torch.float16, want_f32=False, rows=None, row_stride=None):
+def layernorm(x, w, b, eps, out_dtype=torch.float16, want_f32=False, rows=None, row_stride=None, hilo=False):
+    """hilo=True: y16 is the [rows, 2D] hi|lo operand of a split GEMM (lo = 16-bit(y - hi))."""
     _need_cuda(x, w, b)
     D = w.numel()
     if rows is None:
         rows = x.numel() // D
         row_stride = D
-    y16 = torch.empty(rows, D, dtype=out_dtype, device=x.device) if out_dtype is not None else None
+    y16 = torch.empty(rows, 2 * D if hilo else D, dtype=out_dtype, device=x.device) if out_dtype is not None else None
     y32 = torch.empty(rows, D, dtype=torch.float32, device=x.device) if want_f32 else None
     L = _lib.lib()
-    _lib.check(
-        L.keepb200_op_layernorm(
-            x.data_ptr(), row_stride, rows, D, w.data_ptr(), b.data_ptr(), eps, _lib.ptr(y16),
-            1 if out_dtype == torch.bfloat16 else 0, _lib.ptr(y32), _lib.stream_ptr(x.device),
-        ),
-        "op_layernorm",
-    )
+    with _on(x):
+        _lib.check(
+            L.keepb200_op_layernorm(
+                x.data_ptr(), row_stride, rows, D, w.data_ptr(), b.data_ptr(), eps, _lib.ptr(y16),
+                1 if out_dtype == torch.bfloat16 else 0, _lib.ptr(y32), 2 * D if hilo else D, D if hilo else 0,
+                _lib.stream_ptr(x.device),
+            ),
+            "op_layernorm",
+        )
     return y16, y32
 
 
-def attention(qkv, B, S, H, key_mask=None, scale=0.125):
-    """qkv [B*S, 3*H*64] 16-bit -> context [B*S, H*64]."""
+def attention(qkv, B, S, H, key_mask=None, scale=0.125, hilo=False):
+    """qkv [B*S, 3*H*64] 16-bit -> context [B*S, H*64] (hilo=True: [B*S, 2*H*64] = [hi | rounding remainder])."""
     _need_cuda(qkv, key_mask)
-    out = torch.empty(B * S, H * 64, dtype=qkv.dtype, device=qkv.device)
+    out = torch.empty(B * S, (2 if hilo else 1) * H * 64, dtype=qkv.dtype, device=qkv.device)
     L = _lib.lib()
-    _lib.check(
-        L.keepb200_op_attention(
-            qkv.data_ptr(), out.data_ptr(), B, S, H, _is_bf16(qkv), _lib.ptr(key_mask),
-            key_mask.stride(0) if key_mask is not None else 0, scale, _lib.stream_ptr(qkv.device),
-        ),
-        "op_attention",
-    )
+    with _on(qkv):
+        _lib.check(
+            L.keepb200_op_attention(
+                qkv.data_ptr(), out.data_ptr(), B, S, H, _is_bf16(qkv), _lib.ptr(key_mask),
+                key_mask.stride(0) if key_mask is not None else 0, scale, out.stride(0), H * 64 if hilo else 0,
+                _lib.stream_ptr(qkv.device),
+            ),
+            "op_attention",
+        )
+    return out
+
+
+def cast_hilo(w32, dtype=torch.float16):
+    """fp32 [rows, K] -> 16-bit [rows, 2K] = [hi | lo], lo = 16-bit(w - hi): the operand layout of the split GEMMs."""
+    _need_cuda(w32)
+    w32 = w32.contiguous().float()
+    rows, K = w32.shape
+    out = torch.empty(rows, 2 * K, dtype=dtype, device=w32.device)
+    with _on(w32):
+        _lib.check(_lib.lib().keepb200_op_cast_hilo(w32.data_ptr(), out.data_ptr(), rows, K, 1 if dtype == torch.bfloat16 else 0,
+                                                    _lib.stream_ptr(w32.device)), "op_cast_hilo")
+    return out
+
+
+def gemm_split(a, w, K, epi, split, bias=None, resid=None, hilo_out=False):
+    """Split-operand GEMM: a [M, K or 2K], w [N, 2K] hi|lo (ops.cast_hilo); epi as ops.gemm or EPI_BIAS_GELU_HILO."""
+    _need_cuda(a, w, bias, resid)
+    M, N = a.shape[0], w.shape[0]
+    bf = _is_bf16(a)
+    if epi in (EPI_BIAS_HALF, EPI_BIAS_GELU_HALF, EPI_BIAS_GELU_HILO):
+        out = torch.empty(M, 2 * N if epi == EPI_BIAS_GELU_HILO else N, dtype=a.dtype, device=a.device)
+    else:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    with _on(a):
+        _lib.check(
+            _lib.lib().keepb200_op_gemm_split(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, epi, bf, split,
+                                              _lib.ptr(bias), _lib.ptr(resid), resid.stride(0) if resid is not None else 0,
+                                              out.data_ptr(), out.stride(0), N if epi == EPI_BIAS_GELU_HILO else 0,
+                                              _lib.stream_ptr(a.device)),
+            "op_gemm_split",
+        )
+    return out
+
+
+def visual_head(x, lnw, lnb, eps, w0, b0, w1, b1):
+    """normalize(w1 @ gelu(w0 @ LayerNorm(x) + b0) + b1) in one fp32 kernel; w0 [N0, D], w1 [N1, N0] (torch layout)."""
+    _need_cuda(x, lnw, lnb, w0, b0, w1, b1)
+    x = x.contiguous().float()
+    n, D = x.shape
+    out = torch.empty(n, w1.shape[0], dtype=torch.float32, device=x.device)
+    w0t, w1t = w0.t().contiguous().float(), w1.t().contiguous().float()
+    with _on(x):
+        _lib.check(
+            _lib.lib().keepb200_op_visual_head(x.data_ptr(), D, n, D, lnw.data_ptr(), lnb.data_ptr(), eps, w0t.data_ptr(),
+                                               b0.data_ptr(), w0.shape[0], w1t.data_ptr(), b1.data_ptr(), w1.shape[0],
+                                               out.data_ptr(), _lib.stream_ptr(x.device)),
+            "op_visual_head",
+        )
+    return out
+
+
+def pooler(x, w, b):
+    """normalize(tanh(w @ x + b)) in one fp32 kernel; w [D, D] (torch layout)."""
+    _need_cuda(x, w, b)
+    x = x.contiguous().float()
+    n, D = x.shape
+    out = torch.empty(n, D, dtype=torch.float32, device=x.device)
+    wt = w.t().contiguous().float()
+    with _on(x):
+        _lib.check(_lib.lib().keepb200_op_pooler(x.data_ptr(), D, n, D, wt.data_ptr(), b.data_ptr(), out.data_ptr(),
+                                                 _lib.stream_ptr(x.device)), "op_pooler")
     return out
 
 
@@ -150,7 +230,8 @@ def act_l2norm(x, act=0):
     _need_cuda(x)
     y = torch.empty_like(x)
     L = _lib.lib()
-    _lib.check(L.keepb200_op_act_l2norm(x.data_ptr(), x.shape[0], x.shape[1], act, y.data_ptr(), _lib.stream_ptr(x.device)), "op_act_l2norm")
+    with _on(x):
+        _lib.check(L.keepb200_op_act_l2norm(x.data_ptr(), x.shape[0], x.shape[1], act, y.data_ptr(), _lib.stream_ptr(x.device)), "op_act_l2norm")
     return y
 
 
@@ -168,16 +249,18 @@ def similarity(feats, cls, group=0, temp=10.0, want_probs=True, tensor_cores=Tru
     L = _lib.lib()
     ws_bytes = L.keepb200_similarity_workspace_bytes(D, P) if tensor_cores else 0
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=feats.device) if tensor_cores else None
-    _lib.check(
-        L.keepb200_similarity(feats.data_ptr(), N, D, cls.data_ptr(), P, group, temp, logits.data_ptr(), _lib.ptr(probs),
-                              _lib.ptr(ws), ws_bytes, _lib.stream_ptr(feats.device)),
-        "similarity",
-    )
+    with _on(feats):
+        _lib.check(
+            L.keepb200_similarity(feats.data_ptr(), N, D, cls.data_ptr(), P, group, temp, logits.data_ptr(), _lib.ptr(probs),
+                                  _lib.ptr(ws), ws_bytes, _lib.stream_ptr(feats.device)),
+            "similarity",
+        )
     return logits, probs
 
 
-def prompt_scores(feats, cls, K, C, workspace_mb=256):
-    """scores[k] = mean_n(top1 - top2 - |top1 + top2 - 1|) of normalize(feats) @ cls[:, k*C:(k+1)*C]."""
+def prompt_scores(feats, cls, K, C, workspace_mb=256, fused=False):
+    """scores[k] = mean_n(top1 - top2 - |top1 + top2 - 1|) of normalize(feats) @ cls[:, k*C:(k+1)*C] (deterministic).
+    fused=True: the margin is reduced inside the similarity epilogue, the logits never reach memory (C in {2,4,8,16})."""
     _need_cuda(feats, cls)
     feats = feats.contiguous().float()
     cls = cls.contiguous().float()
@@ -189,11 +272,12 @@ def prompt_scores(feats, cls, K, C, workspace_mb=256):
     minimum = L.keepb200_prompt_scores_workspace_bytes(64, D, K, C)  # ... + 64 rows of logits (chunked)
     ws_bytes = max(minimum, min(full, (workspace_mb << 20) + minimum))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=feats.device)
-    _lib.check(
-        L.keepb200_prompt_scores(feats.data_ptr(), N, D, cls.data_ptr(), K, C, scores.data_ptr(), ws.data_ptr(), ws_bytes,
-                                 _lib.stream_ptr(feats.device)),
-        "prompt_scores",
-    )
+    with _on(feats):
+        _lib.check(
+            L.keepb200_prompt_scores(feats.data_ptr(), N, D, cls.data_ptr(), K, C, 1 if fused else 0, scores.data_ptr(),
+                                     ws.data_ptr(), ws_bytes, _lib.stream_ptr(feats.device)),
+            "prompt_scores",
+        )
     return scores
 
 
@@ -208,9 +292,10 @@ def refine(coords, probs, patch_size, overlap):
     L = _lib.lib()
     ws_bytes = L.keepb200_refine_workspace_bytes(N)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=probs.device)
-    _lib.check(
-        L.keepb200_refine(coords.data_ptr(), probs.data_ptr(), N, Cc, patch_size, 1 if overlap else 0, keep.data_ptr(),
-                          refined.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(probs.device)),
-        "refine",
-    )
+    with _on(probs):
+        _lib.check(
+            L.keepb200_refine(coords.data_ptr(), probs.data_ptr(), N, Cc, patch_size, 1 if overlap else 0, keep.data_ptr(),
+                              refined.data_ptr(), ws.data_ptr(), ws_bytes, _lib.stream_ptr(probs.device)),
+            "refine",
+        )
     return keep, refined

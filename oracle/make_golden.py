@@ -58,6 +58,10 @@ def reference_model_namespace():
     return mod.__dict__
 
 
+LAYER_TOKENS_IMAGE = [0, 1, 98, 196]  # CLS, first / middle / last patch
+LAYER_TOKENS_TEXT = [0, 1, 4, 8]       # [CLS] and three attended positions (config 1 prompts have 9-12 tokens)
+
+
 def weight_checksum(sd) -> np.ndarray:
     """Order-independent digest of a state-dict: float64 [sum, sum of squares, sum of |x|*index-hash]."""
     acc = np.zeros(3, dtype=np.float64)
@@ -145,8 +149,22 @@ def make_model_goldens():
     assert len(sd) == 546, len(sd)
     ref_full.load_state_dict(sd, strict=True)
     tiles, text = full_inputs(tile16)
+    # per-layer activations of the reference class for config 1: the residual stream after every
+    # ViT block / BERT layer, sampled at LAYER_TOKENS (the whole stream would be 38 MB)
+    vis_layers, txt_layers = [], []
+    hooks = [blk.register_forward_hook(lambda m, i, o: vis_layers.append(o[:, LAYER_TOKENS_IMAGE].clone()))
+             for blk in ref_full.visual.blocks]
+    hooks += [lay.register_forward_hook(lambda m, i, o: txt_layers.append((o[0] if isinstance(o, tuple) else o)[:, LAYER_TOKENS_TEXT].clone()))
+              for lay in ref_full.text.encoder.layer]
     with torch.no_grad():
         out = ref_full(tiles, text)
+    for h in hooks:
+        h.remove()
+    assert len(vis_layers) == 24 and len(txt_layers) == 12
+    np.savez_compressed(os.path.join(OUT, "keep_full_layers.npz"),
+                        vision_layers=torch.stack(vis_layers).numpy(), text_layers=torch.stack(txt_layers).numpy(),
+                        image_tokens=np.asarray(LAYER_TOKENS_IMAGE), text_tokens=np.asarray(LAYER_TOKENS_TEXT))
+    with torch.no_grad():
         trunk = ref_full.visual(tiles)
         pooled = ref_full.text(**text).pooler_output
     np.savez_compressed(
@@ -322,6 +340,9 @@ if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
     if len(sys.argv) > 1 and sys.argv[1] == "transform":
         make_transform_goldens()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "model":
+        make_model_goldens()
         sys.exit(0)
     make_wsi_goldens()
     make_model_goldens()

@@ -22,7 +22,7 @@ def test_library_builds_and_loads():
     path = build.build()
     assert path.exists()
     L = _lib.lib()
-    assert L.keepb200_version() == 1
+    assert L.keepb200_version() == _lib.ABI_VERSION == 2
 
 
 def test_every_declared_symbol_is_exported_and_bound():
@@ -46,6 +46,24 @@ def test_library_contains_blackwell_kernels():
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", str(_lib.lib_path())], capture_output=True, text=True).stdout
+
+
+def test_no_environment_switch_changes_the_numerics():
+    """The shipped library reads no environment variable (numerics are selected by arguments only), and has one GEMM
+    code path per shape: no multicast-cluster / dynamic-scheduler / wide-epilogue variants left in the binary."""
+    import glob
+
+    for src in glob.glob(os.path.join(ROOT, "keep_b200", "csrc", "*.cu")) + glob.glob(os.path.join(ROOT, "keep_b200", "csrc", "*.h")):
+        assert "getenv" not in open(src).read(), src
+    # (the statically linked CUDA runtime imports getenv for its own CUDA_* variables: the sources are what is checked)
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if os.path.exists(cuobjdump):
+        sass_names = subprocess.run([cuobjdump, "-sass", str(_lib.lib_path())], capture_output=True, text=True).stdout
+        names = set(re.findall(r"Function : (\S+)", sass_names))
+        assert not [n for n in names if "gemm2d" in n], "dynamic-scheduler GEMM variant still compiled"
+        pair = [n for n in names if re.search(r"\d+gemm2_kernelI", n)]
+        single = [n for n in names if re.search(r"\d+gemm_kernelI", n)]
+        assert len(pair) == 9 and len(single) == 9, (pair, single)  # one instantiation per epilogue and main-loop variant
 
 
 def test_config_struct_layout_matches_header():

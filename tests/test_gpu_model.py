@@ -1,9 +1,16 @@
 """GPU: encode_image / encode_text / forward through the C ABI against the CPU oracle (fp32) and the golden
 vectors produced by the reference class (tests/golden, oracle/make_golden.py).
 
-Tolerance (SURVEY.md §8d parity gate): fp16 operands with fp32 accumulation/residual/LayerNorm/softmax:
-per-embedding rel-L2 <= 2e-3 and cosine >= 0.99999; similarity matrix max-abs <= 1e-3. bf16 operands are
-reported against a looser 2e-2 (bf16 has 3 fewer mantissa bits; torch's own bf16 autocast lands at ~1e-2)."""
+Tolerance (north_star: 1e-3 relative): per-embedding rel-L2 against the fp32 oracle and cosine >= 0.99999,
+similarity matrix max-abs <= 1e-3.
+  * text tower (default precision "auto" = split-operand GEMMs for prompt sets of WSI size): TEXT_REL = 5e-4
+    (measured ~3e-4; what is left is the 16-bit q/k/v/P of the attention, oracle/precision_model.py);
+  * text tower, "fast" (one MMA pass, prompt banks): FAST_REL = 2e-3 (measured ~1.4e-3: the 2^-11 operand rounding of
+    24 GEMM inputs per layer stack with no LayerScale to damp it);
+  * image tower: IMAGE_REL = 1e-3. fp16 operands, fp32 accumulate/residual/LayerNorm/softmax; the CLS-row tail of the last
+    block runs split-operand and the head in fp32, the 23.5 blocks before it carry the inherent fp16 operand rounding
+    (torch's own fp16 autocast of this ViT-L: 1.2e-3).
+bf16 operands are reported against a looser 2e-2 (3 fewer mantissa bits; torch's own bf16 autocast lands at ~1e-2)."""
 import numpy as np
 import pytest
 import torch
@@ -12,7 +19,8 @@ from tests import common
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-FP16_REL, FP16_COS, SIM_ABS = 2e-3, 0.99999, 1e-3
+IMAGE_REL, TEXT_REL, FAST_REL, FP16_COS, SIM_ABS = 1e-3, 5e-4, 2e-3, 0.99999, 1e-3
+FP16_REL = IMAGE_REL  # the north-star gate: both towers are held to it (the text tower to the tighter TEXT_REL as well)
 
 
 @pytest.fixture(scope="module")
@@ -66,8 +74,8 @@ def test_full_model_config1_vs_golden(full_pair, golden_dir):
     rl_i, cos_i = common.row_metrics(img, torch.from_numpy(g["vision_features"]))
     rl_t, cos_t = common.row_metrics(txt, torch.from_numpy(g["text_features"]))
     print(f"config1 fp16: image rel-L2 {rl_i:.2e} cos {cos_i:.7f}; text rel-L2 {rl_t:.2e} cos {cos_t:.7f}")
-    assert rl_i <= FP16_REL and cos_i >= FP16_COS
-    assert rl_t <= FP16_REL and cos_t >= FP16_COS
+    assert rl_i <= IMAGE_REL and cos_i >= FP16_COS
+    assert rl_t <= TEXT_REL and cos_t >= FP16_COS
     sim = (img @ txt.T).cpu().numpy()
     assert np.abs(sim - g["similarity"]).max() <= SIM_ABS
 
@@ -87,16 +95,15 @@ def test_full_model_batch_vs_oracle(full_pair):
     txt = prod.encode_text(common.to_device(text, DEV))
     rl_i, cos_i = common.row_metrics(img, ref_i)
     rl_t, cos_t = common.row_metrics(txt, ref_t)
-    assert rl_i <= FP16_REL and cos_i >= FP16_COS, (rl_i, cos_i)
-    assert rl_t <= FP16_REL and cos_t >= FP16_COS, (rl_t, cos_t)
+    print(f"7 tiles / 9 prompts: image rel-L2 {rl_i:.2e}; text rel-L2 {rl_t:.2e}")
+    assert rl_i <= IMAGE_REL and cos_i >= FP16_COS, (rl_i, cos_i)
+    assert rl_t <= TEXT_REL and cos_t >= FP16_COS, (rl_t, cos_t)
 
 
 def test_fused_layernorm_paths_match_standalone_layernorm(full_pair):
-    """The image path folds norm1 (KEEPB200_LN_FUSE=1, default) or norm1 and norm2 (=2) into the following GEMMs
-    (EPI_LN_*); =0 runs the stand-alone LayerNorm kernel in every block. All three must sit inside the parity gate
-    and agree with each other."""
-    import os
-
+    """The image path folds norm1 (mode 1, default) or norm1 and norm2 (mode 2) into the following GEMMs (EPI_LN_*); mode 0
+    runs the stand-alone LayerNorm kernel in every block (keepb200_debug_set_ln_fuse). All three must sit inside the
+    parity gate and agree with each other."""
     oracle, prod, _ = full_pair
     g = torch.Generator().manual_seed(7)
     tiles = torch.randn(5, 3, 224, 224, generator=g)
@@ -105,16 +112,16 @@ def test_fused_layernorm_paths_match_standalone_layernorm(full_pair):
     outs = {}
     try:
         for mode in ("0", "1", "2"):
-            os.environ["KEEPB200_LN_FUSE"] = mode
+            prod.debug_set_ln_fuse(int(mode))
             outs[mode] = prod.encode_image(tiles.to(DEV)).clone()
     finally:
-        del os.environ["KEEPB200_LN_FUSE"]
+        prod.debug_set_ln_fuse(1)
     for mode, out in outs.items():
         rl, cos = common.row_metrics(out, ref)
         rl0, _ = common.row_metrics(out, outs["0"])
-        print(f"KEEPB200_LN_FUSE={mode}: rel-L2 vs fp32 oracle {rl:.2e} (cos {cos:.7f}); vs stand-alone LN {rl0:.2e}")
-        assert rl <= FP16_REL and cos >= FP16_COS, (mode, rl, cos)
-        assert rl0 <= FP16_REL
+        print(f"ln_fuse={mode}: rel-L2 vs fp32 oracle {rl:.2e} (cos {cos:.7f}); vs stand-alone LN {rl0:.2e}")
+        assert rl <= 1.2e-3 and cos >= FP16_COS, (mode, rl, cos)  # mode 2 is a measured-and-rejected variant: looser
+        assert rl0 <= 1.2e-3
     assert not torch.equal(outs["0"], outs["1"]) and not torch.equal(outs["1"], outs["2"])  # the toggle switches paths
     assert torch.equal(outs["1"], prod.encode_image(tiles.to(DEV)))  # default = mode 1, and deterministic
 
@@ -154,7 +161,66 @@ def test_text_trimming_matches_padded_computation(tiny_pair):
     with torch.no_grad():
         ref = oracle.encode_text(text)
     rl, cos = common.row_metrics(trimmed, ref)
-    assert rl <= FP16_REL and cos >= FP16_COS
+    assert rl <= TEXT_REL and cos >= FP16_COS
+
+
+def test_text_precision_modes(full_pair):
+    """text_precision: "high" (split-operand GEMMs) vs "fast" (one pass) vs "auto" on the BERT-base tower; the
+    reference's own call pattern - ONE prompt per call (WSI_evaluation/utils.py:67-74) - must equal the batched result."""
+    from oracle import keep_oracle as ko
+
+    oracle, prod, _ = full_pair
+    text = ko.synthetic_text_inputs(12, seq_len=256, seed=21)
+    with torch.no_grad():
+        ref = oracle.encode_text(text)
+    dtext = common.to_device(text, DEV)
+    res = {}
+    old = prod.config.text_precision
+    try:
+        for mode in ("high", "fast", "auto"):
+            prod.config.text_precision = mode
+            res[mode] = prod.encode_text(dtext).clone()
+        prod.config.text_precision = "bogus"
+        with pytest.raises(ValueError):
+            prod.encode_text(dtext)
+    finally:
+        prod.config.text_precision = old
+    rl_h, _ = common.row_metrics(res["high"], ref)
+    rl_f, cos_f = common.row_metrics(res["fast"], ref)
+    print(f"text tower rel-L2 vs fp32 oracle: high {rl_h:.2e}, fast {rl_f:.2e}")
+    assert rl_h <= TEXT_REL and rl_f <= FAST_REL and cos_f >= FP16_COS
+    assert rl_h < 0.5 * rl_f                               # the split operands are what buys the accuracy
+    assert torch.equal(res["auto"], res["high"])           # 12 prompts <= 8192: auto = high
+    one = prod.encode_text({k: v[5:6] for k, v in dtext.items()})   # batch-1 call, as the reference builds classifiers
+    assert (one - res["auto"][5:6]).abs().max().item() < 2e-5
+
+
+def test_per_layer_parity_table(full_pair, golden_dir):
+    """Where the error comes from: the residual stream after every ViT block / BERT layer (config 1) against the
+    activations of the reference class itself (tests/golden/keep_full_layers.npz, oracle/make_golden.py)."""
+    oracle, prod, _ = full_pair
+    g = common.load_golden(golden_dir, "keep_full.npz")
+    gl = common.load_golden(golden_dir, "keep_full_layers.npz")
+    tiles, text = common.full_inputs(torch.from_numpy(g["example_tile_f16"]))
+    vis, img = prod.debug_layer_outputs(image_inputs=tiles.to(DEV))
+    txt_layers, txt = prod.debug_layer_outputs(text_inputs=common.to_device(text, DEV))
+    it, tt = gl["image_tokens"].tolist(), gl["text_tokens"].tolist()
+    rows = []
+    for i, ref in enumerate(torch.from_numpy(gl["vision_layers"])):          # [2, 4, 1024] per block
+        got = vis[i][:, it] if i < 23 else vis[i][:, None]                      # the last block keeps the CLS rows only
+        ref = ref if i < 23 else ref[:, :1]
+        rows.append(common.rel_l2(got.reshape(-1, 1024), ref.reshape(-1, 1024)))
+    print("ViT residual stream rel-L2 per block:", " ".join(f"{r:.1e}" for r in rows))
+    assert max(rows) <= IMAGE_REL and rows[0] < 5e-4
+    trows = []
+    for i, ref in enumerate(torch.from_numpy(gl["text_layers"])):            # [3, 4, 768] per layer
+        got = txt_layers[i][:, tt] if i < 11 else txt_layers[i][:, None]
+        ref = ref if i < 11 else ref[:, :1]
+        trows.append(common.rel_l2(got.reshape(-1, 768), ref.reshape(-1, 768)))
+    print("BERT hidden states rel-L2 per layer:", " ".join(f"{r:.1e}" for r in trows))
+    assert max(trows) <= TEXT_REL
+    # the dumps do not disturb the results
+    assert torch.equal(img, prod.encode_image(tiles.to(DEV))) and torch.equal(txt, prod.encode_text(common.to_device(text, DEV)))
 
 
 def test_text_optional_inputs(tiny_pair):
@@ -168,7 +234,7 @@ def test_text_optional_inputs(tiny_pair):
         ref = oracle.encode_text(only_ids)
     got = prod.encode_text(common.to_device(only_ids, DEV))
     rl, _ = common.row_metrics(got, ref)
-    assert rl <= FP16_REL
+    assert rl <= TEXT_REL
 
 
 def test_uint8_nhwc_tiles_match_float_path(tiny_pair):
@@ -226,6 +292,10 @@ def test_errors_are_loud(tiny_pair):
     ids = torch.full((2, 8), 5, dtype=torch.long, device=DEV)
     with pytest.raises(ValueError, match="no attended position"):
         prod.encode_text({"input_ids": ids, "attention_mask": torch.tensor([[1, 1, 0, 0, 0, 0, 0, 0], [0] * 8], device=DEV)})
+    with pytest.raises(IndexError, match="input_ids"):   # nn.Embedding raises; clamping would give plausible garbage
+        prod.encode_text({"input_ids": torch.full((1, 4), 1000, dtype=torch.long, device=DEV)})
+    with pytest.raises(IndexError, match="token_type_ids"):
+        prod.encode_text({"input_ids": ids, "token_type_ids": torch.full((2, 8), 2, dtype=torch.long, device=DEV)})
     bad = dict(sd)
     bad.pop("visual.norm.weight")
     from keep_b200 import KEEPConfig, KEEPModel
@@ -249,7 +319,7 @@ def test_raw_uint8_tiles_through_transform_and_tower(full_pair, golden_dir):
     out = prod.encode_image(preprocess(raw[None].to(DEV)))
     rl, cos = common.row_metrics(out, ref)
     print(f"example.tif raw pixels -> embedding: rel-L2 {rl:.2e} cos {cos:.7f}")
-    assert rl <= FP16_REL and cos >= FP16_COS
+    assert rl <= IMAGE_REL and cos >= FP16_COS
 
 
 def test_extreme_shapes_match_oracle(full_pair):
@@ -268,7 +338,7 @@ def test_extreme_shapes_match_oracle(full_pair):
                            (prod.encode_image(tile.to(DEV)), ref_tile, "352x352 tile")):
         rl, cos = common.row_metrics(got, ref)
         print(f"{what}: rel-L2 {rl:.2e} cos {cos:.7f}")
-        assert rl <= FP16_REL and cos >= FP16_COS, (what, rl, cos)
+        assert rl <= (IMAGE_REL if "tile" in what else TEXT_REL) and cos >= FP16_COS, (what, rl, cos)
     empty = {k: v[:0] for k, v in common.to_device(long, DEV).items()}
     assert prod.encode_text(empty).shape == (0, 768)
     assert prod.encode_image(torch.zeros(0, 3, 224, 224, device=DEV)).shape == (0, 768)
