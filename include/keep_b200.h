@@ -56,19 +56,28 @@ extern "C" {
 #define KEEPB200_TILES_F32_NCHW 0 /* float [B,3,H,W], already ImageNet-normalised (keep_inference.py:88-93) */
 #define KEEPB200_TILES_U8_NHWC 1  /* uint8 [B,H,W,3] raw RGB; ToTensor+Normalize fused into the patch gather */
 
-/* precision of keepb200_encode_text. HIGH: every GEMM of the text tower runs split-operand (activations and weights as
- * hi + lo 16-bit pairs, three tensor-core passes into the same fp32 accumulator): ~3e-4 rel-L2 against the fp32 reference
- * instead of ~1.4e-3, at three times the MMA work - nothing for the few thousand prompts of a WSI classifier bank.
- * FAST: one pass (prompt banks of 1e5 prompts). AUTO: HIGH when the call encodes at most
- * KEEPB200_TEXT_AUTO_MAX_PROMPTS prompts, FAST otherwise (a function of P only). */
-#define KEEPB200_TEXT_AUTO 0
-#define KEEPB200_TEXT_HIGH 1
-#define KEEPB200_TEXT_FAST 2
+/* Precision of keepb200_encode_image / keepb200_encode_text (operands are 16-bit either way; accumulation, residual
+ * stream, LayerNorm and softmax are always fp32).
+ *   FAST: every GEMM makes one tensor-core pass over 16-bit operands: the 2^-11 operand rounding shows as ~1.0-1.2e-3
+ *         rel-L2 on the image embedding and ~1.4e-3 on the text embedding against the fp32 reference (torch's own fp16
+ *         autocast of the same ViT-L: 1.2e-3). This is the throughput path (tiles/s, prompt banks).
+ *   HIGH: split-operand GEMMs: activations and weights are carried as hi + lo 16-bit pairs and every GEMM makes three
+ *         passes into the same fp32 accumulator (Ah.Wh + Al.Wh + Ah.Wl): ~2.6e-4 / ~3e-4 rel-L2, at three times the MMA
+ *         work. What stays 16-bit is the attention's q, k, v and probabilities.
+ *   AUTO: HIGH when the call is small enough for the extra passes not to matter - at most
+ *         KEEPB200_IMAGE_AUTO_MAX_TILES tiles (quick-start / interactive use: latency-bound either way) or
+ *         KEEPB200_TEXT_AUTO_MAX_PROMPTS prompts (every WSI classifier bank) - FAST otherwise. A function of the call's
+ *         item count only. The CLS-row tail of the last ViT block and both heads are always computed at HIGH / fp32. */
+#define KEEPB200_PRECISION_AUTO 0
+#define KEEPB200_PRECISION_HIGH 1
+#define KEEPB200_PRECISION_FAST 2
+#define KEEPB200_IMAGE_AUTO_MAX_TILES 16
 #define KEEPB200_TEXT_AUTO_MAX_PROMPTS 8192
 
 /* ops for keepb200_workspace_bytes */
-#define KEEPB200_OP_ENCODE_IMAGE 0
+#define KEEPB200_OP_ENCODE_IMAGE 0      /* FAST */
 #define KEEPB200_OP_ENCODE_TEXT 1
+#define KEEPB200_OP_ENCODE_IMAGE_HIGH 2 /* HIGH: hi|lo activations double the 16-bit buffers */
 
 /* Model geometry. Mirrors KEEPConfig (keep_inference.py:9-22): vision_config is fixed by the timm call at
  * keep_inference.py:32-40 (ViT-L/16), text_config is the BertConfig dict, projection_dim = 768. */
@@ -120,14 +129,16 @@ size_t keepb200_workspace_bytes(void* handle, int op, int64_t n, int64_t seq_len
 
 /* out[B, proj_dim] fp32, unit L2 norm = normalize(visual_head(ViT(tiles)))  (keep_inference.py:54-58).
  * The batch is processed in chunks as large as the workspace allows (>= 1 tile). */
-int keepb200_encode_image(void* handle, const void* tiles, int layout, int64_t B, float* out, void* workspace,
-                          size_t workspace_bytes, void* stream);
+int keepb200_encode_image(void* handle, const void* tiles, int layout, int64_t B, int precision, float* out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+/* how AUTO resolves for a call of B tiles (1 = HIGH): callers size the workspace with it */
+int keepb200_image_precision_is_high(int precision, int64_t B);
 /* Tiles of another size, H and W multiples of 16 with (H/16)*(W/16) + 1 <= 512 tokens: the reference builds its ViT with
  * dynamic_img_size=True (keep_inference.py:39), i.e. timm resamples pos_embed to the new patch grid (bicubic, antialias,
  * prefix token kept). keepb200_encode_image == this call with H = W = img_size. */
-size_t keepb200_workspace_bytes_hw(void* handle, int64_t n, int64_t H, int64_t W);
-int keepb200_encode_image_hw(void* handle, const void* tiles, int layout, int64_t B, int64_t H, int64_t W, float* out,
-                             void* workspace, size_t workspace_bytes, void* stream);
+size_t keepb200_workspace_bytes_hw(void* handle, int64_t n, int64_t H, int64_t W, int high);
+int keepb200_encode_image_hw(void* handle, const void* tiles, int layout, int64_t B, int64_t H, int64_t W, int precision,
+                             float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The reference's input transform for raw RGB tiles of any size (keep_inference.py:88-90; WSI scripts :38-41):
  * Resize(size, BICUBIC) on the PIL image (short side -> size, aspect kept) then CenterCrop(size). tiles: uint8 [B,H,W,3],
@@ -141,7 +152,8 @@ int keepb200_preprocess_u8(const uint8_t* tiles, int64_t B, int64_t H, int64_t W
 /* out[P, hidden] fp32, unit L2 norm = normalize(BertModel(ids, type_ids, mask).pooler_output)
  * (keep_inference.py:60-62). ids/type_ids/mask are int64 [P,S] row-major (type_ids or mask may be NULL:
  * zeros / ones). `s_eff` (1..S) is the number of leading positions to compute: positions >= s_eff must be
- * masked in every row, in which case the result is identical to the padded computation; pass S to disable. */
+ * masked in every row, in which case the result is identical to the padded computation; pass S to disable.
+ * precision: KEEPB200_PRECISION_* above. */
 int keepb200_encode_text(void* handle, const int64_t* ids, const int64_t* type_ids, const int64_t* mask, int64_t P,
                          int64_t S, int64_t s_eff, int precision, float* out, void* workspace, size_t workspace_bytes,
                          void* stream);

@@ -58,9 +58,10 @@ SIGNATURES = {
     "keepb200_weight_name": (C.c_char_p, [_p, _int]),
     "keepb200_finalize": (_int, [_p]),
     "keepb200_workspace_bytes": (_sz, [_p, _int, _i64, _i64]),
-    "keepb200_encode_image": (_int, [_p, _p, _int, _i64, _p, _p, _sz, _p]),
-    "keepb200_workspace_bytes_hw": (_sz, [_p, _i64, _i64, _i64]),
-    "keepb200_encode_image_hw": (_int, [_p, _p, _int, _i64, _i64, _i64, _p, _p, _sz, _p]),
+    "keepb200_encode_image": (_int, [_p, _p, _int, _i64, _int, _p, _p, _sz, _p]),
+    "keepb200_image_precision_is_high": (_int, [_int, _i64]),
+    "keepb200_workspace_bytes_hw": (_sz, [_p, _i64, _i64, _i64, _int]),
+    "keepb200_encode_image_hw": (_int, [_p, _p, _int, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
     "keepb200_preprocess_workspace_bytes": (_sz, [_i64, _i64, _i64, _int]),
     "keepb200_preprocess_u8": (_int, [_p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
     "keepb200_encode_text": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _sz, _p]),
@@ -92,7 +93,7 @@ SIGNATURES = {
 }
 
 ABI_VERSION = 2  # KEEPB200_ABI_VERSION of include/keep_b200.h
-TEXT_AUTO, TEXT_HIGH, TEXT_FAST = 0, 1, 2
+PRECISION = {"auto": 0, "high": 1, "fast": 2}  # KEEPB200_PRECISION_*
 
 _LIB = None
 

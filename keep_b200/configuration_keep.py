@@ -19,17 +19,19 @@ class KEEPConfig(PretrainedConfig):
     model_type = "keep"
 
     def __init__(self, vision_config=None, text_config=None, projection_dim=768, operand_dtype="float16",
-                 text_precision="auto", **kwargs):
+                 text_precision="auto", image_precision="auto", **kwargs):
         super().__init__(**kwargs)
         self.vision_config = vision_config
         self.text_config = text_config
         self.projection_dim = projection_dim
         # keep_b200 extensions.  operand_dtype: 16-bit type of the tensor-core operands ("float16" | "bfloat16").
-        # text_precision: "high" = split-operand GEMMs through the whole text tower (hi + lo 16-bit pairs, ~3e-4 rel-L2
-        # against the fp32 reference, three MMA passes), "fast" = one pass (~1.4e-3), "auto" = high for calls of up to
-        # 8192 prompts (every WSI classifier bank), fast for larger prompt banks.
+        # text_precision / image_precision (include/keep_b200.h KEEPB200_PRECISION_*): "high" = split-operand GEMMs
+        # through the whole tower (hi + lo 16-bit pairs, three MMA passes: ~3e-4 rel-L2 against the fp32 reference),
+        # "fast" = one pass (~1.0-1.4e-3: the fp16 operand rounding; the throughput path), "auto" = high for calls of up
+        # to 8192 prompts (every WSI classifier bank) / 16 tiles (quick-start use), fast for anything larger.
         self.operand_dtype = operand_dtype
         self.text_precision = text_precision
+        self.image_precision = image_precision
 
     # resolved geometry ---------------------------------------------------------------------------
     def vision(self) -> dict:

@@ -21,6 +21,7 @@ struct WeightSlot {
   std::vector<int64_t> shape;  // reference shape
   bool as16 = false;           // converted to the 16-bit operand dtype (GEMM weights)
   bool hilo = false;           // ... as a [N, 2K] hi|lo operand (split-operand GEMMs, common.h GEMM_SPLIT_*)
+  void* dst_hl = nullptr;      // a second, hi|lo copy next to the plain 16-bit one (ViT weights: fast and high-precision paths)
   void* dst = nullptr;         // device destination (base of the owning allocation + offset)
   bool loaded = false;
   bool ignored = false;        // accepted but unused (logit_scale: dead at inference)
@@ -29,8 +30,8 @@ struct WeightSlot {
 
 struct VitBlock {
   float *n1w, *n1b, *qkv_b, *proj_b, *ls1, *n2w, *n2b, *fc1_b, *fc2_b, *ls2;
-  void *qkv_w, *proj_w, *fc1_w, *fc2_w;
-  int wmul = 1;  // 2: proj_w / fc1_w / fc2_w are [N, 2K] hi|lo operands (the last block: its CLS-row tail runs split)
+  void *qkv_w, *proj_w, *fc1_w, *fc2_w;      // plain 16-bit [N, K]: the one-pass path
+  void *qkv_hl, *proj_hl, *fc1_hl, *fc2_hl;  // [N, 2K] hi|lo: the split-operand path (image_precision high; CLS-row tail)
   // LayerNorm folded into the following Linear (EPI_LN_*): 16-bit W * ln.weight, column sums, b.W^T + bias
   void *qkv_wf = nullptr, *fc1_wf = nullptr;
   float *qkv_s = nullptr, *qkv_c = nullptr, *fc1_s = nullptr, *fc1_c = nullptr;
@@ -49,7 +50,7 @@ struct Model {
   std::vector<void*> allocs;
   // vision
   float *cls = nullptr, *pos = nullptr, *pe_b = nullptr, *norm_w = nullptr, *norm_b = nullptr;
-  void* pe_w = nullptr;
+  void *pe_w = nullptr, *pe_hl = nullptr;
   std::vector<VitBlock> blocks;
   float *h0_w = nullptr, *h2_w = nullptr, *h0_b = nullptr, *h2_b = nullptr;  // visual_head in fp32 (head.cu)
   float *h0_wt = nullptr, *h2_wt = nullptr;                                  // ... transposed [K, N] at finalize
@@ -108,6 +109,15 @@ int new_w16(Model* m, const std::string& name, std::vector<int64_t> shape, void*
   m->slots.back().hilo = hilo;
   return KB_OK;
 }
+// plain 16-bit [N, K] and hi|lo [N, 2K] copies of the same weight
+int new_w16_both(Model* m, const std::string& name, std::vector<int64_t> shape, void** plain, void** hl) {
+  size_t n = 1;
+  for (auto d : shape) n *= (size_t)d;
+  KB_TRY(new_w16(m, name, std::move(shape), plain, false));
+  KB_TRY(alloc_dev(m, n * 4, hl));
+  m->slots.back().dst_hl = *hl;
+  return KB_OK;
+}
 
 // the slot registered last (a GEMM weight) also keeps an fp32 master and gets a LayerNorm-folded twin
 int add_fold(Model* m, size_t N, size_t K, void** wf, float** s_vec, float** c_vec) {
@@ -128,7 +138,7 @@ int build_tables(Model* m) {
   // ---- vision tower: timm vit_large_patch16_224 state-dict ----
   KB_TRY(new_f32(m, "visual.cls_token", {1, 1, D}, &m->cls));
   KB_TRY(new_f32(m, "visual.pos_embed", {1, T, D}, &m->pos));
-  KB_TRY(new_w16(m, "visual.patch_embed.proj.weight", {D, 3, ps, ps}, &m->pe_w));
+  KB_TRY(new_w16_both(m, "visual.patch_embed.proj.weight", {D, 3, ps, ps}, &m->pe_w, &m->pe_hl));
   KB_TRY(new_f32(m, "visual.patch_embed.proj.bias", {D}, &m->pe_b));
   m->blocks.resize(c.vit_depth);
   for (int i = 0; i < c.vit_depth; ++i) {
@@ -136,20 +146,18 @@ int build_tables(Model* m) {
     const std::string p = "visual.blocks." + std::to_string(i) + ".";
     KB_TRY(new_f32(m, p + "norm1.weight", {D}, &b.n1w));
     KB_TRY(new_f32(m, p + "norm1.bias", {D}, &b.n1b));
-    KB_TRY(new_w16(m, p + "attn.qkv.weight", {3 * D, D}, &b.qkv_w));
+    KB_TRY(new_w16_both(m, p + "attn.qkv.weight", {3 * D, D}, &b.qkv_w, &b.qkv_hl));
     KB_TRY(add_fold(m, (size_t)3 * D, D, &b.qkv_wf, &b.qkv_s, &b.qkv_c));
     KB_TRY(new_f32(m, p + "attn.qkv.bias", {3 * D}, &b.qkv_b));
-    const bool last = (i + 1 == c.vit_depth);
-    b.wmul = last ? 2 : 1;
-    KB_TRY(new_w16(m, p + "attn.proj.weight", {D, D}, &b.proj_w, last));
+    KB_TRY(new_w16_both(m, p + "attn.proj.weight", {D, D}, &b.proj_w, &b.proj_hl));
     KB_TRY(new_f32(m, p + "attn.proj.bias", {D}, &b.proj_b));
     KB_TRY(new_f32(m, p + "ls1.gamma", {D}, &b.ls1));
     KB_TRY(new_f32(m, p + "norm2.weight", {D}, &b.n2w));
     KB_TRY(new_f32(m, p + "norm2.bias", {D}, &b.n2b));
-    KB_TRY(new_w16(m, p + "mlp.fc1.weight", {F, D}, &b.fc1_w, last));
+    KB_TRY(new_w16_both(m, p + "mlp.fc1.weight", {F, D}, &b.fc1_w, &b.fc1_hl));
     KB_TRY(add_fold(m, (size_t)F, D, &b.fc1_wf, &b.fc1_s, &b.fc1_c));
     KB_TRY(new_f32(m, p + "mlp.fc1.bias", {F}, &b.fc1_b));
-    KB_TRY(new_w16(m, p + "mlp.fc2.weight", {D, F}, &b.fc2_w, last));
+    KB_TRY(new_w16_both(m, p + "mlp.fc2.weight", {D, F}, &b.fc2_w, &b.fc2_hl));
     KB_TRY(new_f32(m, p + "mlp.fc2.bias", {D}, &b.fc2_b));
     KB_TRY(new_f32(m, p + "ls2.gamma", {D}, &b.ls2));
   }
@@ -259,20 +267,21 @@ struct ImageWs {
   size_t x, xn, qkv, att, hid, xc, cls16, stats, pos, total;
 };
 // gh x gw = patch grid of the tiles (the model's own grid unless dynamic_img_size is exercised)
-ImageWs image_ws(const Model* m, int64_t n, int gh, int gw) {
+// high: every 16-bit activation that feeds a GEMM is a [rows, 2*width] hi|lo operand (split-operand path)
+ImageWs image_ws(const Model* m, int64_t n, int gh, int gw, bool high) {
   const KeepB200Config& c = m->cfg;
   const size_t T = (size_t)gh * gw + 1;
   const size_t M = (size_t)n * T;
-  const size_t D = c.vit_width, F = c.vit_mlp;
-  const size_t patch_bytes = (size_t)n * (T - 1) * 768 * 2;
+  const size_t D = c.vit_width, F = c.vit_mlp, hl = high ? 2 : 1;
+  const size_t patch_bytes = (size_t)n * (T - 1) * 768 * 2 * hl;
   ImageWs w;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   w.x = take(M * D * 4);
-  w.xn = take(M * D * 2);
+  w.xn = take(M * D * 2 * hl);
   w.qkv = take(M * 3 * D * 2);
   w.att = take(M * D * 2);
-  size_t hid_bytes = M * F * 2;  // also holds the [n, 2F] hi|lo hidden of the CLS-row tail (T >= 2)
+  size_t hid_bytes = M * F * 2 * hl;  // also holds the [n, 2F] hi|lo hidden of the CLS-row tail (T >= 2)
   if (patch_bytes > hid_bytes) hid_bytes = patch_bytes;  // the patch matrix aliases the MLP hidden buffer
   w.hid = take(hid_bytes);
   w.xc = take((size_t)n * D * 4);  // CLS rows of the residual stream (last block onwards)
@@ -349,12 +358,12 @@ int dump_layer(Model* m, int index, size_t slot_floats, const float* src, size_t
   return KB_OK;
 }
 
-int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, int gh, int gw, float* out, char* ws,
+int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, int gh, int gw, bool high, float* out, char* ws,
                        cudaStream_t st) {
   const KeepB200Config& c = m->cfg;
   const int bf = c.operand_dtype, D = c.vit_width, F = c.vit_mlp, T = gh * gw + 1;
   const int M = (int)(n * T);
-  const ImageWs w = image_ws(m, n, gh, gw);
+  const ImageWs w = image_ws(m, n, gh, gw, high);
   float* x = reinterpret_cast<float*>(ws + w.x);
   void* xn = ws + w.xn;
   void* qkv = ws + w.qkv;
@@ -377,20 +386,37 @@ int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, int g
   }
   // patch gather (+ CLS rows), then patch-embed GEMM scattering into x[b, 1+p, :] with +bias +pos
   if (layout == KEEPB200_TILES_F32_NCHW)
-    KB_TRY(launch_im2col(static_cast<const float*>(tiles), n, gh, gw, hid, bf, m->cls, pos, x, D, st));
+    KB_TRY(launch_im2col(static_cast<const float*>(tiles), n, gh, gw, hid, bf, m->cls, pos, x, D, st, high));
   else
-    KB_TRY(launch_im2col_u8(static_cast<const uint8_t*>(tiles), n, gh, gw, hid, bf, m->cls, pos, x, D, st));
-  KB_TRY(G(hid, m->pe_w, (int)(n * (T - 1)), D, 768, EPI_PATCH_F32, bf, x, D).bias(m->pe_b).patch(pos, T - 1).run(st));
+    KB_TRY(launch_im2col_u8(static_cast<const uint8_t*>(tiles), n, gh, gw, hid, bf, m->cls, pos, x, D, st, high));
+  if (high)
+    KB_TRY(G(hid, m->pe_hl, (int)(n * (T - 1)), D, 768, EPI_PATCH_F32, bf, x, D).bias(m->pe_b).patch(pos, T - 1)
+               .pitch(1536, 1536).split(GEMM_SPLIT_AW).run(st));
+  else
+    KB_TRY(G(hid, m->pe_w, (int)(n * (T - 1)), D, 768, EPI_PATCH_F32, bf, x, D).bias(m->pe_b).patch(pos, T - 1).run(st));
   for (int i = 0; i < c.vit_depth; ++i) {
     const VitBlock& b = m->blocks[i];
-    if (fuse >= 1 && i > 0) {
+    if (high) {
+      // split-operand path: stand-alone LayerNorm kernels emit hi|lo rows, every GEMM makes three passes over hi|lo
+      // operands; what stays 16-bit is the attention (q, k, v, P and the context) - oracle/precision_model.py
+      KB_TRY(launch_layernorm(x, D, M, D, b.n1w, b.n1b, c.vit_ln_eps, xn, bf, nullptr, st, 2 * D, D));
+      KB_TRY(G(xn, b.qkv_hl, M, 3 * D, D, EPI_BIAS_HALF, bf, qkv, 3 * D).bias(b.qkv_b).pitch(2 * D, 2 * D).split(GEMM_SPLIT_AW).run(st));
+    } else if (fuse >= 1 && i > 0) {
       KB_TRY(gemm_ln(xn, D, b.qkv_wf, M, 3 * D, EPI_LN_BIAS_HALF, bf, b.qkv_c, b.qkv_s, stats, c.vit_ln_eps, qkv, st));
     } else {
       KB_TRY(launch_layernorm(x, D, M, D, b.n1w, b.n1b, c.vit_ln_eps, xn, bf, nullptr, st));
       KB_TRY(G(xn, b.qkv_w, M, 3 * D, D, EPI_BIAS_HALF, bf, qkv, 3 * D).bias(b.qkv_b).run(st));
     }
     KB_TRY(launch_attention(qkv, att, (int)n, T, c.vit_heads, bf, nullptr, 0, 0.125f, st));
-    if (i + 1 < c.vit_depth && fuse == 2) {
+    if (i + 1 < c.vit_depth && high) {
+      KB_TRY(G(att, b.proj_hl, M, D, D, EPI_RESID_F32, bf, x, D).bias(b.proj_b).gamma(b.ls1).resid(x).pitch(D, 2 * D)
+                 .split(GEMM_SPLIT_W).run(st));
+      KB_TRY(launch_layernorm(x, D, M, D, b.n2w, b.n2b, c.vit_ln_eps, xn, bf, nullptr, st, 2 * D, D));
+      KB_TRY(G(xn, b.fc1_hl, M, F, D, EPI_BIAS_GELU_HILO, bf, hid, 2 * F).bias(b.fc1_b).pitch(2 * D, 2 * D)
+                 .split(GEMM_SPLIT_AW).lo(F).run(st));
+      KB_TRY(G(hid, b.fc2_hl, M, D, F, EPI_RESID_F32, bf, x, D).bias(b.fc2_b).gamma(b.ls2).resid(x).pitch(2 * F, 2 * F)
+                 .split(GEMM_SPLIT_AW).run(st));
+    } else if (i + 1 < c.vit_depth && fuse == 2) {
       KB_TRY(gemm_resid_stats(att, b.proj_w, M, D, D, bf, b.proj_b, b.ls1, x, xn, stats, st));
       KB_TRY(gemm_ln(xn, D, b.fc1_wf, M, F, EPI_LN_BIAS_GELU_HALF, bf, b.fc1_c, b.fc1_s, stats, c.vit_ln_eps, hid, st));
       KB_TRY(gemm_resid_stats(hid, b.fc2_w, M, D, F, bf, b.fc2_b, b.ls2, x, xn, stats, st));
@@ -405,15 +431,15 @@ int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, int g
     } else {
       // Last block: only the CLS token is consumed downstream (global_pool='token'), and everything after the
       // attention is row-wise, so proj / norm2 / fc1 / fc2 run on the n CLS rows (row pitch T*D) only. At n rows the
-      // MMA time is nothing, so these GEMMs run split-operand (hi|lo weights, hi|lo LayerNorm / GELU outputs):
+      // MMA time is nothing, so these GEMMs always run split-operand (hi|lo weights, hi|lo LayerNorm / GELU outputs):
       // the tail adds no 2^-11 operand rounding of its own to the embedding.
       const int64_t pitch = (int64_t)T * D;
-      KB_TRY(G(att, b.proj_w, (int)n, D, D, EPI_RESID_F32, bf, xc, D).bias(b.proj_b).gamma(b.ls1).resid(x, pitch)
+      KB_TRY(G(att, b.proj_hl, (int)n, D, D, EPI_RESID_F32, bf, xc, D).bias(b.proj_b).gamma(b.ls1).resid(x, pitch)
                  .pitch(pitch, 2 * D).split(GEMM_SPLIT_W).run(st));
       KB_TRY(launch_layernorm(xc, D, n, D, b.n2w, b.n2b, c.vit_ln_eps, cls16, bf, nullptr, st, 2 * D, D));
-      KB_TRY(G(cls16, b.fc1_w, (int)n, F, D, EPI_BIAS_GELU_HILO, bf, hid, 2 * F).bias(b.fc1_b).pitch(2 * D, 2 * D)
+      KB_TRY(G(cls16, b.fc1_hl, (int)n, F, D, EPI_BIAS_GELU_HILO, bf, hid, 2 * F).bias(b.fc1_b).pitch(2 * D, 2 * D)
                  .split(GEMM_SPLIT_AW).lo(F).run(st));
-      KB_TRY(G(hid, b.fc2_w, (int)n, D, F, EPI_RESID_F32, bf, xc, D).bias(b.fc2_b).gamma(b.ls2).resid(xc)
+      KB_TRY(G(hid, b.fc2_hl, (int)n, D, F, EPI_RESID_F32, bf, xc, D).bias(b.fc2_b).gamma(b.ls2).resid(xc)
                  .pitch(2 * F, 2 * F).split(GEMM_SPLIT_AW).run(st));
     }
     if (i + 1 < c.vit_depth) KB_TRY(dump_layer(m, i, (size_t)M * D, x, (size_t)M * D, st));
@@ -549,6 +575,8 @@ int keepb200_load_weight(void* handle, const char* name, const float* data, cons
   for (auto d : s.shape) n *= (size_t)d;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (s.master != nullptr) KB_CUDA_CHECK(cudaMemcpyAsync(s.master, data, n * 4, cudaMemcpyDeviceToDevice, st));
+  if (s.dst_hl != nullptr)
+    KB_TRY(launch_cast_f32_to_hilo(data, s.dst_hl, s.shape[0], (int)(n / (size_t)s.shape[0]), m->cfg.operand_dtype, st));
   if (s.as16 && s.hilo)
     KB_TRY(launch_cast_f32_to_hilo(data, s.dst, s.shape[0], (int)(n / (size_t)s.shape[0]), m->cfg.operand_dtype, st));
   else if (s.as16)
@@ -598,7 +626,8 @@ int keepb200_finalize(void* handle) {
 size_t keepb200_workspace_bytes(void* handle, int op, int64_t n, int64_t seq_len) {
   if (!handle || n <= 0) return 0;
   Model* m = static_cast<Model*>(handle);
-  if (op == KEEPB200_OP_ENCODE_IMAGE) return image_ws(m, n, m->grid(), m->grid()).total;
+  if (op == KEEPB200_OP_ENCODE_IMAGE) return image_ws(m, n, m->grid(), m->grid(), false).total;
+  if (op == KEEPB200_OP_ENCODE_IMAGE_HIGH) return image_ws(m, n, m->grid(), m->grid(), true).total;
   if (op == KEEPB200_OP_ENCODE_TEXT) return text_ws(m, n, seq_len > 0 ? seq_len : m->cfg.max_pos).total;
   return 0;
 }
@@ -616,16 +645,20 @@ static int check_hw(const Model* m, int64_t H, int64_t W, int* gh, int* gw) {
   return KB_OK;
 }
 
-size_t keepb200_workspace_bytes_hw(void* handle, int64_t n, int64_t H, int64_t W) {
+size_t keepb200_workspace_bytes_hw(void* handle, int64_t n, int64_t H, int64_t W, int high) {
   if (!handle || n <= 0) return 0;
   Model* m = static_cast<Model*>(handle);
   int gh, gw;
   if (check_hw(m, H, W, &gh, &gw) != KB_OK) return 0;
-  return image_ws(m, n, gh, gw).total;
+  return image_ws(m, n, gh, gw, high != 0).total;
 }
 
-int keepb200_encode_image_hw(void* handle, const void* tiles, int layout, int64_t B, int64_t H, int64_t W, float* out,
-                             void* workspace, size_t workspace_bytes, void* stream) {
+int keepb200_image_precision_is_high(int precision, int64_t B) {
+  return precision == KEEPB200_PRECISION_HIGH || (precision == KEEPB200_PRECISION_AUTO && B <= KEEPB200_IMAGE_AUTO_MAX_TILES);
+}
+
+int keepb200_encode_image_hw(void* handle, const void* tiles, int layout, int64_t B, int64_t H, int64_t W, int precision,
+                             float* out, void* workspace, size_t workspace_bytes, void* stream) {
   if (!handle) return set_error(KB_ERR_ARG, "null handle");
   Model* m = static_cast<Model*>(handle);
   if (!m->finalized) return set_error(KB_ERR_STATE, "encode_image: handle not finalised");
@@ -633,10 +666,14 @@ int keepb200_encode_image_hw(void* handle, const void* tiles, int layout, int64_
   if (B < 0 || !tiles || !out) return set_error(KB_ERR_ARG, "encode_image: bad arguments");
   if (layout != KEEPB200_TILES_F32_NCHW && layout != KEEPB200_TILES_U8_NHWC)
     return set_error(KB_ERR_ARG, "encode_image: unknown tile layout %d", layout);
+  if (precision != KEEPB200_PRECISION_AUTO && precision != KEEPB200_PRECISION_HIGH && precision != KEEPB200_PRECISION_FAST)
+    return set_error(KB_ERR_ARG, "encode_image: unknown precision %d", precision);
+  // AUTO is a function of the call's tile count only (never of the workspace or the chunking)
+  const bool high = keepb200_image_precision_is_high(precision, B) != 0;
   int gh, gw;
   KB_TRY(check_hw(m, H, W, &gh, &gw));
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return set_error(KB_ERR_ARG, "encode_image: workspace must be 1024-byte aligned");
-  const size_t per1 = image_ws(m, 1, gh, gw).total;
+  const size_t per1 = image_ws(m, 1, gh, gw, high).total;
   if (!workspace || workspace_bytes < per1)
     return set_error(KB_ERR_WORKSPACE, "encode_image: workspace %zu B < %zu B needed for one tile", workspace_bytes, per1);
   // largest chunk that fits (the layout is monotone in n); rows are limited to int32 GEMM extents
@@ -644,8 +681,8 @@ int keepb200_encode_image_hw(void* handle, const void* tiles, int layout, int64_
   int64_t chunk = B;
   const int64_t max_rows = (int64_t)1 << 30;
   if (chunk * T > max_rows) chunk = max_rows / T;
-  while (chunk > 1 && image_ws(m, chunk, gh, gw).total > workspace_bytes) {
-    int64_t guess = (int64_t)(workspace_bytes / (image_ws(m, chunk, gh, gw).total / (double)chunk));
+  while (chunk > 1 && image_ws(m, chunk, gh, gw, high).total > workspace_bytes) {
+    int64_t guess = (int64_t)(workspace_bytes / (image_ws(m, chunk, gh, gw, high).total / (double)chunk));
     chunk = guess < chunk ? (guess > 1 ? guess : 1) : chunk - 1;
   }
   const size_t tile_elems = (size_t)3 * H * W;
@@ -653,17 +690,17 @@ int keepb200_encode_image_hw(void* handle, const void* tiles, int layout, int64_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {
     const int64_t n = (B - b0 < chunk) ? (B - b0) : chunk;
-    KB_TRY(encode_image_chunk(m, static_cast<const char*>(tiles) + (size_t)b0 * tile_bytes, layout, n, gh, gw,
+    KB_TRY(encode_image_chunk(m, static_cast<const char*>(tiles) + (size_t)b0 * tile_bytes, layout, n, gh, gw, high,
                               out + (size_t)b0 * m->cfg.proj_dim, static_cast<char*>(workspace), st));
   }
   return KB_OK;
 }
 
-int keepb200_encode_image(void* handle, const void* tiles, int layout, int64_t B, float* out, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+int keepb200_encode_image(void* handle, const void* tiles, int layout, int64_t B, int precision, float* out,
+                          void* workspace, size_t workspace_bytes, void* stream) {
   if (!handle) return set_error(KB_ERR_ARG, "null handle");
   const Model* m = static_cast<Model*>(handle);
-  return keepb200_encode_image_hw(handle, tiles, layout, B, m->cfg.img_size, m->cfg.img_size, out, workspace,
+  return keepb200_encode_image_hw(handle, tiles, layout, B, m->cfg.img_size, m->cfg.img_size, precision, out, workspace,
                                   workspace_bytes, stream);
 }
 
@@ -679,10 +716,10 @@ int keepb200_encode_text(void* handle, const int64_t* ids, const int64_t* type_i
     return set_error(KB_ERR_ARG, "encode_text: sequence length %lld outside [1, %d]", (long long)S,
                      m->cfg.max_pos < 512 ? m->cfg.max_pos : 512);
   if (s_eff < 1 || s_eff > S) return set_error(KB_ERR_ARG, "encode_text: s_eff %lld outside [1, %lld]", (long long)s_eff, (long long)S);
-  if (precision != KEEPB200_TEXT_AUTO && precision != KEEPB200_TEXT_HIGH && precision != KEEPB200_TEXT_FAST)
+  if (precision != KEEPB200_PRECISION_AUTO && precision != KEEPB200_PRECISION_HIGH && precision != KEEPB200_PRECISION_FAST)
     return set_error(KB_ERR_ARG, "encode_text: unknown precision %d", precision);
   // AUTO is a function of the call's prompt count only (never of the workspace or the chunking)
-  const bool precise = precision == KEEPB200_TEXT_HIGH || (precision == KEEPB200_TEXT_AUTO && P <= KEEPB200_TEXT_AUTO_MAX_PROMPTS);
+  const bool precise = precision == KEEPB200_PRECISION_HIGH || (precision == KEEPB200_PRECISION_AUTO && P <= KEEPB200_TEXT_AUTO_MAX_PROMPTS);
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return set_error(KB_ERR_ARG, "encode_text: workspace must be 1024-byte aligned");
   const size_t per1 = text_ws(m, 1, s_eff).total;
   if (!workspace || workspace_bytes < per1)

@@ -145,11 +145,12 @@ int launch_attention_tc(const void* qkv, void* out, int B, int S, int H, int bf1
 // ---- ViT front end ----------------------------------------------------------------------------------------
 // tiles fp32 NCHW [B,3,Gh*16,Gw*16] -> patches16 [B*Gh*Gw, 768] (col = c*256+ky*16+kx); also writes the CLS
 // rows x[b*(Gh*Gw+1), :] = cls + pos[0].
+// hilo != 0: patches16 is [B*Gh*Gw, 1536] = [hi | rounding remainder] (split-operand patch embedding)
 int launch_im2col(const float* tiles, int64_t B, int Gh, int Gw, void* patches16, int bf16, const float* cls,
-                  const float* pos, float* x, int D, cudaStream_t stream);
+                  const float* pos, float* x, int D, cudaStream_t stream, int hilo = 0);
 // uint8 NHWC tiles [B,H,W,3] with fused (x/255-mean)/std
 int launch_im2col_u8(const uint8_t* tiles, int64_t B, int Gh, int Gw, void* patches16, int bf16, const float* cls,
-                     const float* pos, float* x, int D, cudaStream_t stream);
+                     const float* pos, float* x, int D, cudaStream_t stream, int hilo = 0);
 // pos_embed [1 + G0*G0, D] -> out [1 + Gh*Gw, D]: prefix row copied, grid rows resampled (bicubic, antialias)
 int launch_pos_resample(const float* pos, int G0, int Gh, int Gw, int D, float* out, cudaStream_t stream);
 

@@ -26,7 +26,7 @@ __device__ __forceinline__ uint32_t pk(float a, float b, int bf16) {
 
 // one thread = 8 consecutive pixels of one image row of one channel
 __global__ void im2col_f32_kernel(const float* __restrict__ tiles, long long total, int Gh, int G, uint16_t* __restrict__ patches,
-                                  int bf16) {
+                                  int bf16, int pitch, int lo_off) {
   const int W = G * 16, H = Gh * 16, X8 = W / 8;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -43,13 +43,21 @@ __global__ void im2col_f32_kernel(const float* __restrict__ tiles, long long tot
     uint4 w;
     w.x = pk(v0.x, v0.y, bf16); w.y = pk(v0.z, v0.w, bf16);
     w.z = pk(v1.x, v1.y, bf16); w.w = pk(v1.z, v1.w, bf16);
-    *reinterpret_cast<uint4*>(patches + row * 768 + c * 256 + ky * 16 + kx) = w;
+    uint16_t* dst = patches + row * pitch + c * 256 + ky * 16 + kx;
+    *reinterpret_cast<uint4*>(dst) = w;
+    if (lo_off > 0) {  // rounding remainders: the patch matrix becomes the hi|lo operand of a split-operand patch embedding
+      const float2 h0 = unpk(w.x, bf16), h1 = unpk(w.y, bf16), h2 = unpk(w.z, bf16), h3 = unpk(w.w, bf16);
+      uint4 l;
+      l.x = pk(v0.x - h0.x, v0.y - h0.y, bf16); l.y = pk(v0.z - h1.x, v0.w - h1.y, bf16);
+      l.z = pk(v1.x - h2.x, v1.y - h2.y, bf16); l.w = pk(v1.z - h3.x, v1.w - h3.y, bf16);
+      *reinterpret_cast<uint4*>(dst + lo_off) = l;
+    }
   }
 }
 
 // one thread = 8 consecutive pixels (24 bytes, all 3 channels) of one image row
 __global__ void im2col_u8_kernel(const uint8_t* __restrict__ tiles, long long total, int Gh, int G, uint16_t* __restrict__ patches,
-                                 int bf16) {
+                                 int bf16, int pitch, int lo_off) {
   const int W = G * 16, H = Gh * 16, X8 = W / 8;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float istd[3] = {1.f / 0.229f, 1.f / 0.224f, 1.f / 0.225f};
@@ -73,7 +81,15 @@ __global__ void im2col_u8_kernel(const uint8_t* __restrict__ tiles, long long to
       uint4 w;
       w.x = pk(f[0], f[1], bf16); w.y = pk(f[2], f[3], bf16);
       w.z = pk(f[4], f[5], bf16); w.w = pk(f[6], f[7], bf16);
-      *reinterpret_cast<uint4*>(patches + row * 768 + c * 256 + ky * 16 + kx) = w;
+      uint16_t* dst = patches + row * pitch + c * 256 + ky * 16 + kx;
+      *reinterpret_cast<uint4*>(dst) = w;
+      if (lo_off > 0) {
+        const float2 h0 = unpk(w.x, bf16), h1 = unpk(w.y, bf16), h2 = unpk(w.z, bf16), h3 = unpk(w.w, bf16);
+        uint4 l;
+        l.x = pk(f[0] - h0.x, f[1] - h0.y, bf16); l.y = pk(f[2] - h1.x, f[3] - h1.y, bf16);
+        l.z = pk(f[4] - h2.x, f[5] - h2.y, bf16); l.w = pk(f[6] - h3.x, f[7] - h3.y, bf16);
+        *reinterpret_cast<uint4*>(dst + lo_off) = l;
+      }
     }
   }
 }
@@ -231,28 +247,30 @@ int launch_pos_resample(const float* pos, int G0, int Gh, int Gw, int D, float* 
 }
 
 int launch_im2col(const float* tiles, int64_t B, int Gh, int G, void* patches16, int bf16, const float* cls,
-                  const float* pos, float* x, int D, cudaStream_t stream) {
+                  const float* pos, float* x, int D, cudaStream_t stream, int hilo) {
   if (B <= 0) return KB_OK;
   const int W = G * 16;
   const long long total = (long long)B * 3 * (Gh * 16) * (W / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 32;
   if (blocks > cap) blocks = cap;
-  im2col_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tiles, total, Gh, G, (uint16_t*)patches16, bf16);
+  im2col_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tiles, total, Gh, G, (uint16_t*)patches16, bf16, hilo ? 1536 : 768,
+                                                          hilo ? 768 : 0);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return launch_cls_rows(cls, pos, x, B, Gh * G + 1, D, stream);
 }
 
 int launch_im2col_u8(const uint8_t* tiles, int64_t B, int Gh, int G, void* patches16, int bf16, const float* cls,
-                     const float* pos, float* x, int D, cudaStream_t stream) {
+                     const float* pos, float* x, int D, cudaStream_t stream, int hilo) {
   if (B <= 0) return KB_OK;
   const int W = G * 16;
   const long long total = (long long)B * (Gh * 16) * (W / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 32;
   if (blocks > cap) blocks = cap;
-  im2col_u8_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tiles, total, Gh, G, (uint16_t*)patches16, bf16);
+  im2col_u8_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tiles, total, Gh, G, (uint16_t*)patches16, bf16, hilo ? 1536 : 768,
+                                                         hilo ? 768 : 0);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return launch_cls_rows(cls, pos, x, B, Gh * G + 1, D, stream);

@@ -194,13 +194,17 @@ class KEEPModel(PreTrainedModel):
         out = torch.empty(B, self.config.projection_dim, dtype=torch.float32, device=dev)
         if B == 0:
             return out
+        precision = _lib.PRECISION.get(str(getattr(self.config, "image_precision", "auto")))
+        if precision is None:
+            raise ValueError(f"image_precision must be 'auto', 'high' or 'fast', got {self.config.image_precision!r}")
         L = _lib.lib()
         with torch.cuda.device(dev):
-            need = L.keepb200_workspace_bytes_hw(self._handle, min(B, self.image_chunk), H, W)
+            high = L.keepb200_image_precision_is_high(precision, B)
+            need = L.keepb200_workspace_bytes_hw(self._handle, min(B, self.image_chunk), H, W, high)
             ws = self._workspace(need, dev)
             _lib.check(
-                L.keepb200_encode_image_hw(self._handle, x.data_ptr(), layout, B, H, W, out.data_ptr(), self._aligned(ws),
-                                           need, _lib.stream_ptr(dev)),
+                L.keepb200_encode_image_hw(self._handle, x.data_ptr(), layout, B, H, W, precision, out.data_ptr(),
+                                           self._aligned(ws), need, _lib.stream_ptr(dev)),
                 "encode_image")
         return out
 
@@ -225,8 +229,7 @@ class KEEPModel(PreTrainedModel):
         out = torch.empty(P, hidden, dtype=torch.float32, device=dev)
         if P == 0:
             return out
-        precision = {"auto": _lib.TEXT_AUTO, "high": _lib.TEXT_HIGH, "fast": _lib.TEXT_FAST}.get(
-            str(getattr(self.config, "text_precision", "auto")))
+        precision = _lib.PRECISION.get(str(getattr(self.config, "text_precision", "auto")))
         if precision is None:
             raise ValueError(f"text_precision must be 'auto', 'high' or 'fast', got {self.config.text_precision!r}")
         s_eff = S

@@ -46,7 +46,8 @@ def test_config2_detection_10k_tiles_x_32_prompts(full_pair):
     with torch.no_grad():
         ref = oracle.encode_image(tiles[idx].cpu())
     rl, cos = common.row_metrics(feats[idx], ref)
-    assert rl <= 2e-3 and cos >= 0.99999, (rl, cos)
+    print(f"config 2, fast path, 6 of the 10k tiles vs the fp32 oracle: rel-L2 {rl:.2e}")
+    assert rl <= 1.25e-3 and cos >= 0.99999, (rl, cos)  # FAST_REL_IMAGE of tests/test_gpu_model.py
     # a different batch split gives the same rows (row independence of every kernel on the path)
     again = prod.encode_image(tiles[700:1500])
     assert (again - feats[700:1500]).abs().max().item() < 1e-5
@@ -168,7 +169,7 @@ def _prompt_bank_checks(oracle, prod, text, dev_text, P):
     with torch.no_grad():
         ref = oracle.encode_text({k: v[idx] for k, v in text.items()})
     rl, cos = common.row_metrics(out[idx], ref)
-    assert rl <= 2e-3 and cos >= 0.99999, (rl, cos)
+    assert rl <= 2e-3 and cos >= 0.99999, (rl, cos)  # FAST_REL_TEXT of tests/test_gpu_model.py
     # trimming to the longest attended position is exact: the padded S=256 computation gives the same bits
     sub = {k: v[20_000:20_512] for k, v in dev_text.items()}
     old = prod.trim_text

@@ -1,15 +1,15 @@
 """GPU: encode_image / encode_text / forward through the C ABI against the CPU oracle (fp32) and the golden
 vectors produced by the reference class (tests/golden, oracle/make_golden.py).
 
-Tolerance (north_star: 1e-3 relative): per-embedding rel-L2 against the fp32 oracle and cosine >= 0.99999,
-similarity matrix max-abs <= 1e-3.
-  * text tower (default precision "auto" = split-operand GEMMs for prompt sets of WSI size): TEXT_REL = 5e-4
-    (measured ~3e-4; what is left is the 16-bit q/k/v/P of the attention, oracle/precision_model.py);
-  * text tower, "fast" (one MMA pass, prompt banks): FAST_REL = 2e-3 (measured ~1.4e-3: the 2^-11 operand rounding of
-    24 GEMM inputs per layer stack with no LayerScale to damp it);
-  * image tower: IMAGE_REL = 1e-3. fp16 operands, fp32 accumulate/residual/LayerNorm/softmax; the CLS-row tail of the last
-    block runs split-operand and the head in fp32, the 23.5 blocks before it carry the inherent fp16 operand rounding
-    (torch's own fp16 autocast of this ViT-L: 1.2e-3).
+Tolerance (north_star: 1e-3 relative): per-embedding rel-L2 against the fp32 oracle and cosine
+>= 0.99999, similarity matrix max-abs <= 1e-3. Two precision levels exist (include/keep_b200.h KEEPB200_PRECISION_*):
+  * HIGH - split-operand GEMMs (hi + lo 16-bit operand pairs, three MMA passes). This is what the default "auto" policy
+    runs for calls of quick-start / WSI-classifier size (<= 16 tiles, <= 8192 prompts): HIGH_REL = 5e-4 for both towers
+    (measured ~2.6e-4 image, ~3e-4 text; what is left is the 16-bit q/k/v/P of the attention, oracle/precision_model.py).
+    A prompt of one single token has no softmax average over keys to damp the rounding of v: it is held to NORTH_STAR.
+  * FAST - one MMA pass over fp16 operands, the throughput path (bulk tiles, prompt banks): FAST_REL_IMAGE = 1.25e-3
+    (measured 1.0-1.2e-3: the inherent 2^-11 rounding of 24 x 4 GEMM operand pairs; torch's own fp16 autocast of this
+    ViT-L lands at 1.2e-3) and FAST_REL_TEXT = 2e-3 (measured ~1.4e-3: post-LN BERT has no LayerScale to damp it).
 bf16 operands are reported against a looser 2e-2 (3 fewer mantissa bits; torch's own bf16 autocast lands at ~1e-2)."""
 import numpy as np
 import pytest
@@ -19,8 +19,29 @@ from tests import common
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-IMAGE_REL, TEXT_REL, FAST_REL, FP16_COS, SIM_ABS = 1e-3, 5e-4, 2e-3, 0.99999, 1e-3
-FP16_REL = IMAGE_REL  # the north-star gate: both towers are held to it (the text tower to the tighter TEXT_REL as well)
+NORTH_STAR = 1e-3
+HIGH_REL, FAST_REL_IMAGE, FAST_REL_TEXT, FP16_COS, SIM_ABS = 5e-4, 1.25e-3, 2e-3, 0.99999, 1e-3
+IMAGE_REL = TEXT_REL = HIGH_REL  # what the default ("auto") policy delivers at the batch sizes of these tests
+FAST_REL = FAST_REL_TEXT
+FP16_REL = NORTH_STAR
+
+
+class precision:
+    """with precision(model, image="fast", text="high"): ... - pin the precision policy of a model for a block."""
+
+    def __init__(self, model, image=None, text=None):
+        self.m, self.new = model, {"image_precision": image, "text_precision": text}
+
+    def __enter__(self):
+        self.old = {k: getattr(self.m.config, k) for k in self.new}
+        for k, v in self.new.items():
+            if v is not None:
+                setattr(self.m.config, k, v)
+        return self.m
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            setattr(self.m.config, k, v)
 
 
 @pytest.fixture(scope="module")
@@ -73,9 +94,10 @@ def test_full_model_config1_vs_golden(full_pair, golden_dir):
     txt = prod.encode_text(common.to_device(text, DEV))
     rl_i, cos_i = common.row_metrics(img, torch.from_numpy(g["vision_features"]))
     rl_t, cos_t = common.row_metrics(txt, torch.from_numpy(g["text_features"]))
-    print(f"config1 fp16: image rel-L2 {rl_i:.2e} cos {cos_i:.7f}; text rel-L2 {rl_t:.2e} cos {cos_t:.7f}")
-    assert rl_i <= IMAGE_REL and cos_i >= FP16_COS
-    assert rl_t <= TEXT_REL and cos_t >= FP16_COS
+    print(f"config1 fp16 (default policy): image rel-L2 {rl_i:.2e} cos {cos_i:.7f}; text rel-L2 {rl_t:.2e} cos {cos_t:.7f}")
+    assert rl_i <= NORTH_STAR and rl_t <= NORTH_STAR           # the north-star gate ...
+    assert rl_i <= HIGH_REL and cos_i >= FP16_COS               # ... and what the split-operand path actually delivers
+    assert rl_t <= HIGH_REL and cos_t >= FP16_COS
     sim = (img @ txt.T).cpu().numpy()
     assert np.abs(sim - g["similarity"]).max() <= SIM_ABS
 
@@ -95,9 +117,15 @@ def test_full_model_batch_vs_oracle(full_pair):
     txt = prod.encode_text(common.to_device(text, DEV))
     rl_i, cos_i = common.row_metrics(img, ref_i)
     rl_t, cos_t = common.row_metrics(txt, ref_t)
-    print(f"7 tiles / 9 prompts: image rel-L2 {rl_i:.2e}; text rel-L2 {rl_t:.2e}")
+    print(f"7 tiles / 9 prompts (auto = high): image rel-L2 {rl_i:.2e}; text rel-L2 {rl_t:.2e}")
     assert rl_i <= IMAGE_REL and cos_i >= FP16_COS, (rl_i, cos_i)
     assert rl_t <= TEXT_REL and cos_t >= FP16_COS, (rl_t, cos_t)
+    with precision(prod, image="fast", text="fast"):   # the throughput path on the same inputs
+        rl_i, cos_i = common.row_metrics(prod.encode_image(tiles.to(DEV)), ref_i)
+        rl_t, cos_t = common.row_metrics(prod.encode_text(common.to_device(text, DEV)), ref_t)
+    print(f"7 tiles / 9 prompts (fast): image rel-L2 {rl_i:.2e}; text rel-L2 {rl_t:.2e}")
+    assert rl_i <= FAST_REL_IMAGE and cos_i >= FP16_COS, (rl_i, cos_i)
+    assert rl_t <= FAST_REL_TEXT and cos_t >= FP16_COS, (rl_t, cos_t)
 
 
 def test_fused_layernorm_paths_match_standalone_layernorm(full_pair):
@@ -111,19 +139,22 @@ def test_fused_layernorm_paths_match_standalone_layernorm(full_pair):
         ref = oracle.encode_image(tiles)
     outs = {}
     try:
-        for mode in ("0", "1", "2"):
-            prod.debug_set_ln_fuse(int(mode))
-            outs[mode] = prod.encode_image(tiles.to(DEV)).clone()
+        with precision(prod, image="fast"):  # the LayerNorm folding belongs to the one-pass path
+            for mode in ("0", "1", "2"):
+                prod.debug_set_ln_fuse(int(mode))
+                outs[mode] = prod.encode_image(tiles.to(DEV)).clone()
+            prod.debug_set_ln_fuse(1)
+            again = prod.encode_image(tiles.to(DEV))
     finally:
         prod.debug_set_ln_fuse(1)
     for mode, out in outs.items():
         rl, cos = common.row_metrics(out, ref)
         rl0, _ = common.row_metrics(out, outs["0"])
         print(f"ln_fuse={mode}: rel-L2 vs fp32 oracle {rl:.2e} (cos {cos:.7f}); vs stand-alone LN {rl0:.2e}")
-        assert rl <= 1.2e-3 and cos >= FP16_COS, (mode, rl, cos)  # mode 2 is a measured-and-rejected variant: looser
-        assert rl0 <= 1.2e-3
+        assert rl <= FAST_REL_IMAGE and cos >= FP16_COS, (mode, rl, cos)
+        assert rl0 <= FAST_REL_IMAGE
     assert not torch.equal(outs["0"], outs["1"]) and not torch.equal(outs["1"], outs["2"])  # the toggle switches paths
-    assert torch.equal(outs["1"], prod.encode_image(tiles.to(DEV)))  # default = mode 1, and deterministic
+    assert torch.equal(outs["1"], again)  # default = mode 1, and deterministic
 
 
 def test_batch_invariance_and_chunking(tiny_pair):
@@ -131,18 +162,26 @@ def test_batch_invariance_and_chunking(tiny_pair):
     _, prod, _, _ = tiny_pair
     g = torch.Generator().manual_seed(3)
     tiles = torch.randn(37, 3, 224, 224, generator=g).to(DEV)
-    whole = prod.encode_image(tiles)
-    old = prod.image_chunk
-    try:
-        prod.image_chunk = 8  # 37 tiles -> 5 chunks, the last one ragged
-        prod._ws = None
-        chunked = prod.encode_image(tiles)
-    finally:
-        prod.image_chunk = old
-        prod._ws = None
-    single = prod.encode_image(tiles[11:12])
-    assert (whole - chunked).abs().max().item() < 1e-5
-    assert (whole[11:12] - single).abs().max().item() < 1e-5
+    for mode in ("fast", "high"):  # within one precision level the result does not depend on batch or chunking
+        with precision(prod, image=mode):
+            whole = prod.encode_image(tiles)
+            old = prod.image_chunk
+            try:
+                prod.image_chunk = 8  # 37 tiles -> 5 chunks, the last one ragged
+                prod._ws = None
+                chunked = prod.encode_image(tiles)
+            finally:
+                prod.image_chunk = old
+                prod._ws = None
+            single = prod.encode_image(tiles[11:12])
+        assert (whole - chunked).abs().max().item() < 1e-5, mode
+        assert (whole[11:12] - single).abs().max().item() < 1e-5, mode
+    # "auto" is a function of the call's tile count alone: 37 tiles run fast, one tile runs high
+    auto37, auto1 = prod.encode_image(tiles), prod.encode_image(tiles[11:12])
+    with precision(prod, image="fast"):
+        assert torch.equal(auto37, prod.encode_image(tiles))
+    with precision(prod, image="high"):
+        assert torch.equal(auto1, prod.encode_image(tiles[11:12]))
 
 
 def test_text_trimming_matches_padded_computation(tiny_pair):
@@ -188,7 +227,7 @@ def test_text_precision_modes(full_pair):
     rl_h, _ = common.row_metrics(res["high"], ref)
     rl_f, cos_f = common.row_metrics(res["fast"], ref)
     print(f"text tower rel-L2 vs fp32 oracle: high {rl_h:.2e}, fast {rl_f:.2e}")
-    assert rl_h <= TEXT_REL and rl_f <= FAST_REL and cos_f >= FP16_COS
+    assert rl_h <= HIGH_REL and rl_f <= FAST_REL_TEXT and cos_f >= FP16_COS
     assert rl_h < 0.5 * rl_f                               # the split operands are what buys the accuracy
     assert torch.equal(res["auto"], res["high"])           # 12 prompts <= 8192: auto = high
     one = prod.encode_text({k: v[5:6] for k, v in dtext.items()})   # batch-1 call, as the reference builds classifiers
@@ -202,25 +241,27 @@ def test_per_layer_parity_table(full_pair, golden_dir):
     g = common.load_golden(golden_dir, "keep_full.npz")
     gl = common.load_golden(golden_dir, "keep_full_layers.npz")
     tiles, text = common.full_inputs(torch.from_numpy(g["example_tile_f16"]))
-    vis, img = prod.debug_layer_outputs(image_inputs=tiles.to(DEV))
-    txt_layers, txt = prod.debug_layer_outputs(text_inputs=common.to_device(text, DEV))
     it, tt = gl["image_tokens"].tolist(), gl["text_tokens"].tolist()
-    rows = []
-    for i, ref in enumerate(torch.from_numpy(gl["vision_layers"])):          # [2, 4, 1024] per block
-        got = vis[i][:, it] if i < 23 else vis[i][:, None]                      # the last block keeps the CLS rows only
-        ref = ref if i < 23 else ref[:, :1]
-        rows.append(common.rel_l2(got.reshape(-1, 1024), ref.reshape(-1, 1024)))
-    print("ViT residual stream rel-L2 per block:", " ".join(f"{r:.1e}" for r in rows))
-    assert max(rows) <= IMAGE_REL and rows[0] < 5e-4
-    trows = []
-    for i, ref in enumerate(torch.from_numpy(gl["text_layers"])):            # [3, 4, 768] per layer
-        got = txt_layers[i][:, tt] if i < 11 else txt_layers[i][:, None]
-        ref = ref if i < 11 else ref[:, :1]
-        trows.append(common.rel_l2(got.reshape(-1, 768), ref.reshape(-1, 768)))
-    print("BERT hidden states rel-L2 per layer:", " ".join(f"{r:.1e}" for r in trows))
-    assert max(trows) <= TEXT_REL
-    # the dumps do not disturb the results
-    assert torch.equal(img, prod.encode_image(tiles.to(DEV))) and torch.equal(txt, prod.encode_text(common.to_device(text, DEV)))
+    for mode, gate_i, gate_t in (("fast", FAST_REL_IMAGE, FAST_REL_TEXT), ("high", HIGH_REL, HIGH_REL)):
+        with precision(prod, image=mode, text=mode):
+            vis, img = prod.debug_layer_outputs(image_inputs=tiles.to(DEV))
+            txt_layers, txt = prod.debug_layer_outputs(text_inputs=common.to_device(text, DEV))
+            rows = []
+            for i, ref in enumerate(torch.from_numpy(gl["vision_layers"])):      # [2, 4, 1024] per block
+                got = vis[i][:, it] if i < 23 else vis[i][:, None]                  # the last block keeps the CLS rows only
+                ref = ref if i < 23 else ref[:, :1]
+                rows.append(common.rel_l2(got.reshape(-1, 1024), ref.reshape(-1, 1024)))
+            print(f"[{mode}] ViT residual stream rel-L2 per block:", " ".join(f"{r:.1e}" for r in rows))
+            assert max(rows) <= gate_i
+            trows = []
+            for i, ref in enumerate(torch.from_numpy(gl["text_layers"])):        # [3, 4, 768] per layer
+                got = txt_layers[i][:, tt] if i < 11 else txt_layers[i][:, None]
+                ref = ref if i < 11 else ref[:, :1]
+                trows.append(common.rel_l2(got.reshape(-1, 768), ref.reshape(-1, 768)))
+            print(f"[{mode}] BERT hidden states rel-L2 per layer:", " ".join(f"{r:.1e}" for r in trows))
+            assert max(trows) <= gate_t
+            # the dumps do not disturb the results
+            assert torch.equal(img, prod.encode_image(tiles.to(DEV))) and torch.equal(txt, prod.encode_text(common.to_device(text, DEV)))
 
 
 def test_text_optional_inputs(tiny_pair):
@@ -259,10 +300,12 @@ def test_dynamic_img_size_matches_oracle(full_pair, H, W):
     tiles = torch.randn(3, 3, H, W, generator=g)
     with torch.no_grad():
         ref = oracle.encode_image(tiles)
-    out = prod.encode_image(tiles.to(DEV))
-    rl, cos = common.row_metrics(out, ref)
-    print(f"{H}x{W}: rel-L2 {rl:.2e} cos {cos:.7f}")
-    assert rl <= FP16_REL and cos >= FP16_COS, (H, W, rl, cos)
+    for mode, gate in (("high", HIGH_REL), ("fast", FAST_REL_IMAGE)):
+        with precision(prod, image=mode):
+            out = prod.encode_image(tiles.to(DEV))
+        rl, cos = common.row_metrics(out, ref)
+        print(f"{H}x{W} {mode}: rel-L2 {rl:.2e} cos {cos:.7f}")
+        assert rl <= gate and cos >= FP16_COS, (H, W, mode, rl, cos)
 
 
 def test_bf16_operands_reported(golden_dir):
@@ -338,7 +381,7 @@ def test_extreme_shapes_match_oracle(full_pair):
                            (prod.encode_image(tile.to(DEV)), ref_tile, "352x352 tile")):
         rl, cos = common.row_metrics(got, ref)
         print(f"{what}: rel-L2 {rl:.2e} cos {cos:.7f}")
-        assert rl <= (IMAGE_REL if "tile" in what else TEXT_REL) and cos >= FP16_COS, (what, rl, cos)
+        assert rl <= (NORTH_STAR if what.startswith("1-token") else HIGH_REL) and cos >= FP16_COS, (what, rl, cos)
     empty = {k: v[:0] for k, v in common.to_device(long, DEV).items()}
     assert prod.encode_text(empty).shape == (0, 768)
     assert prod.encode_image(torch.zeros(0, 3, 224, 224, device=DEV)).shape == (0, 768)
