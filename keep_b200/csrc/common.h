@@ -136,11 +136,12 @@ int launch_pooler(const float* x, int64_t ldx, int64_t n, int D, const float* wt
 int launch_attention(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
                      int64_t mask_stride, float scale, cudaStream_t stream, int64_t out_pitch = 0, int64_t lo_off = 0);
 
-// tcgen05 variant (64 < S <= 224); launch_attention dispatches to it unless KEEPB200_ATTN=v1
-bool attention_tc_supports(int S);
 void attention_tc_set_trace(long long* dev_buf);  // debug aid: clock64 stamps of CTA 0, [64 units][16 events]
-int launch_attention_tc(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
-                        int64_t mask_stride, float scale, cudaStream_t stream);
+// single-tile variant for 64 < S <= 224 (attention_tc1.cu); launch_attention dispatches to it
+bool attention_tc1_supports(int S);
+int launch_attention_tc1(const void* qkv, void* out, int B, int S, int H, int bf16, const int64_t* key_mask,
+                         int64_t mask_stride, float scale, cudaStream_t stream, int64_t out_pitch, int64_t lo_off,
+                         long long* trace);
 
 // ---- ViT front end ----------------------------------------------------------------------------------------
 // tiles fp32 NCHW [B,3,Gh*16,Gw*16] -> patches16 [B*Gh*Gw, 768] (col = c*256+ky*16+kx); also writes the CLS

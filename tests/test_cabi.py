@@ -45,6 +45,8 @@ def test_library_contains_blackwell_kernels():
     sass = subprocess.run([cuobjdump, "-sass", str(_lib.lib_path())], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, mnemonic
+    # no legacy warp-level tensor path left: every MMA in the library is tcgen05 (UTC*MMA); HMMA would be mma.sync
+    assert not re.search(r"\bHMMA\b", sass)
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", str(_lib.lib_path())], capture_output=True, text=True).stdout
 
 

@@ -149,9 +149,14 @@ def test_l2norm_and_tanh():
 
 
 @pytest.mark.parametrize("B,S,H,masked", [(3, 197, 16, False), (5, 256, 12, True), (7, 32, 12, True), (2, 77, 4, True),
-                                            (1, 1, 2, False), (2, 300, 2, True)])
+                                            (1, 1, 2, False), (2, 300, 2, True), (150, 1, 2, True), (23, 5, 3, True),
+                                            (9, 12, 12, True), (40, 33, 2, False), (3, 56, 4, True), (3, 57, 4, True),
+                                            (5, 64, 2, False), (2, 112, 3, True), (2, 113, 3, True), (3, 224, 2, False),
+                                            (2, 225, 2, True), (1, 512, 2, True), (2, 485, 2, False), (300, 197, 1, False)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_attention(B, S, H, masked, dtype):
+    """Every shape class of the tcgen05 kernel: packed sequences (S <= 56, whole sequences of a head share one tile,
+    ragged last group), one to five KV blocks of up to 112 keys, ragged last query tile, key masks of random lengths."""
     from keep_b200 import ops
 
     g = torch.Generator().manual_seed(S * 3 + H)
@@ -165,22 +170,26 @@ def test_attention(B, S, H, masked, dtype):
     out = ops.attention(qkv, B, S, H, key_mask=mask)
     q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
     ref = F.scaled_dot_product_attention(q, k, v, attn_mask=bias, scale=0.125).transpose(1, 2).reshape(B * S, H * 64)
+    assert torch.isfinite(out).all()
     assert _rel(out, ref) < (2e-3 if dtype == torch.float16 else 1.5e-2)
+    assert torch.equal(out, ops.attention(qkv, B, S, H, key_mask=mask))  # deterministic
 
 
-def test_attention_late_maximum_triggers_rescale():
-    """The tcgen05 kernel reads S once with a lazily raised softmax reference; rows whose maximum sits in a late
-    key block, ~2^30 above the first block, must come out identical to the two-pass result."""
+@pytest.mark.parametrize("S,hot", [(197, (150, 196)), (256, (120, 250)), (300, (299, 230)), (40, (39, 20)), (512, (100, 460))])
+def test_attention_late_maximum_in_a_later_block(S, hot):
+    """The lazy softmax reference: rows whose maximum sits in a LATER KV block, ~2^30 above everything before it, after the
+    earlier blocks were already multiplied into O (the O-rescale path), and in a late chunk of the same block."""
     from keep_b200 import ops
 
-    B, S, H = 2, 197, 16
-    g = torch.Generator().manual_seed(77)
+    B, H = 2, 8
+    g = torch.Generator().manual_seed(S)
     qkv = (torch.randn(B * S, 3 * H * 64, generator=g) * 0.5).view(B, S, 3, H, 64)
-    # make key 150 (5th block) align strongly with every query of head 3, and key 196 (masked-path block) with head 5
     qkv[:, :, 0, 3, :] = 3.0
-    qkv[:, 150, 1, 3, :] = 4.0
+    qkv[:, hot[0], 1, 3, :] = 4.0        # one key aligned with every query of head 3
     qkv[:, :, 0, 5, :] = -2.0
-    qkv[:, 196, 1, 5, :] = -5.0
+    qkv[:, hot[1], 1, 5, :] = -5.0       # ... and another one for head 5
+    qkv[:, : S // 2, 0, 6, :] = 2.5       # head 6: only the first half of the queries sees the spike
+    qkv[:, hot[0], 1, 6, :] = 3.0
     qkv = qkv.reshape(B * S, 3 * H * 64).half().to(DEV)
     out = ops.attention(qkv, B, S, H)
     q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
