@@ -19,6 +19,15 @@ The 32 prompt embeddings are produced once by encode_text before the timed regio
            launches), both measured live with CUDA events around every GEMM launch in the timed region
   cpu_baseline / --impl reference: the CPU oracle port of the reference (oracle/keep_oracle.py: the reference
            KEEPModel semantics + restated timm ViT-L/16; timm is not installed) on the host cores, fp32.
+  extra  : the other BASELINE.json configs, measured in the same run (not the headline; `--no-extras` skips them):
+           config3  zeroshot_subtyping_WSI: 50,000 tiles STRONG-scaled over the N ranks (50,000 / N each, ragged last
+                    chunk), 256 prompt columns, fp16 and bf16 operands, the all-gather of the [N,768] embeddings and the
+                    similarity + refine + slide label inside the timed region;
+           config4  zeroshot_segmentation_WSI: 200,000 overlapping tiles / N per rank streamed from pinned uint8 host
+                    batches of 1024 (H2D inside the timed region, ToTensor+Normalize fused into the patch gather), 2 prompt
+                    columns, probabilities gathered, refine_seg on the whole slide;
+           config5  (N = 1) encode_text over the 91,632-prompt bank at seq_len 256: padded and trimmed prompts/s and the
+                    fraction of the BERT tensor roofline (45.904 GFLOP per padded prompt).
 """
 from __future__ import annotations
 
@@ -40,6 +49,8 @@ METRIC = "WSI tiles/sec (224x224, ViT-L/16) zero-shot hot path"
 UNIT = "tiles/s"
 FLOP_PER_TILE = 123.110e9  # SURVEY.md §8d / BASELINE.md §2: ViT-L/16 + visual_head, MAC = 2 FLOP, 197 tokens
 N_TILES, N_PROMPTS, BATCH = 10_000, 32, 1024
+FLOP_PER_PROMPT_PADDED = 45.904e9  # BERT-base at S = 256
+CPU_SAMPLE_TILES = 16              # tiles per step of the CPU reference arm (bounded sample of the same workload)
 
 
 def measured_peaks():
@@ -126,14 +137,19 @@ def cpu_reference_tiles_per_s(sample_tiles: int, steps: int, warmup: int):
 def run_reference_arm(args, rank):
     if rank != 0:
         return 0
-    sample = 16
+    sample = CPU_SAMPLE_TILES
     tps, ms, threads, cpu = cpu_reference_tiles_per_s(sample, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "note": "reference = CPU fp32 path of KEEPModel.encode_image + similarity; timm is "
-                   "un-vendored and not installed, so the ViT-L/16 is the oracle's restatement (oracle/keep_oracle.py)"},
+        "config": {"workload": workload_name(), "sample_tiles_per_step": sample,
+                   "note": "reference arm = the reference's CPU fp32 path (KEEPModel.encode_image + similarity) on a bounded sample "
+                           f"of the workload: {sample} tiles per step instead of {N_TILES} (same metric, same unit). kind 'port': the "
+                           "oracle class (oracle/keep_oracle.py: keep_inference.py:25-73 restated, ViT-L/16 restated because timm is "
+                           "un-vendored and not installed); /root/reference does not travel to the GPU box, so the reference file "
+                           "itself cannot be exec'd here (oracle/make_golden.py does that in the build container and pins the "
+                           "oracle to it, tests/test_oracle.py)"},
         "cpu_baseline": {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample} tiles per step (encode_image + 32-prompt similarity), fp32, {cpu}"},
         "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -183,6 +199,8 @@ def main():
     ap.add_argument("--operand-dtype", default="float16", choices=["float16", "bfloat16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE configs 3/4/5 block")
+    ap.add_argument("--extra-scale", type=float, default=1.0, help="scale the tile/prompt counts of the extras (tests)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "keep_b200" else max(args.warmup, 1)
 

@@ -495,6 +495,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         if (p.G != 0 && live)
           for (int c = 0; c < c_lo; c += 16) tmem_st_32x8(t_row + (c >> 1), zeros);
         const int slow_begin = max(c_lo, fast_end);
+        if (p.G != 0 && live) {
+          // Packed sequences: the reference is the exact row maximum (rounded up to an integer), taken in a pre-pass over
+          // the few columns of the window. A prompt's probabilities - and with them their 16-bit rounding - then do not
+          // depend on which other prompts share its tile or on how far the batch was trimmed: encode_text of one prompt
+          // equals its row in a batched call up to fp32 summation order.
+          float mx = -INFINITY;
+          for (int c = c_lo; c < c_hi; c += 16) {
+            uint32_t v[16];
+            tmem_ld_32x16(t_row + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool mine = (c + i >= my_lo) && (c + i < my_hi);
+              mx = fmaxf(mx, mine ? fmaf(__uint_as_float(v[i]), p.scale_log2, bias[c + i]) : -INFINITY);
+            }
+          }
+          m_ref = mx == -INFINITY ? -INFINITY : ceilf(mx);
+        }
         for (int c = slow_begin; c < c_hi; c += 16) {  // chunks with masked keys (or foreign sequences): additive 0 / -inf bias
           uint32_t v[16];
           tmem_ld_32x16(t_row + c, v);
@@ -513,8 +531,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float e0 = ex2f(t[2 * i] + neg_m), e1 = ex2f(t[2 * i + 1] + neg_m);
-            sum += e0 + e1;
             pk[i] = pack16(e0, e1, p.bf16);
+            // the row sum is taken over the ROUNDED probabilities the PV MMA will see: the weights then sum to exactly one
+            // (with a handful of keys the rounding of P would otherwise scale the whole context row by up to 2^-11)
+            const float2 r = unpack16(pk[i], p.bf16);
+            sum += r.x + r.y;
           }
           tmem_st_32x8(t_row + (c >> 1), pk);
         }

@@ -358,8 +358,13 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float e0 = ex2f(t[2 * i] + neg_m), e1 = ex2f(t[2 * i + 1] + neg_m);
-          sum += e0 + e1;
           pk[i] = pack16(e0, e1, p.bf16);
+          if (p.key_mask != nullptr) {  // masked (text) rows: sum the ROUNDED probabilities, as attention_tc.cu does
+            const float2 r = unpack16(pk[i], p.bf16);
+            sum += r.x + r.y;
+          } else {
+            sum += e0 + e1;
+          }
         }
         tmem_st_32x8(t_row + (c >> 1), pk);
       }

@@ -170,7 +170,11 @@ def _prompt_bank_checks(oracle, prod, text, dev_text, P):
         ref = oracle.encode_text({k: v[idx] for k, v in text.items()})
     rl, cos = common.row_metrics(out[idx], ref)
     assert rl <= 2e-3 and cos >= 0.99999, (rl, cos)  # FAST_REL_TEXT of tests/test_gpu_model.py
-    # trimming to the longest attended position is exact: the padded S=256 computation gives the same bits
+    # Trimming to the longest attended position changes nothing mathematically (masked keys weigh exp(-inf) = 0 and only
+    # the [CLS] row is consumed). The padded S = 256 computation walks its keys in three 112-key blocks instead of packed
+    # 32-key tiles, so its 16-bit attention probabilities are rounded against a different reference and fp32 sums run in
+    # another order: the two one-pass (fp16 operand) results agree to that rounding (measured 6.5e-4; each is ~1.4e-3 from
+    # the fp32 oracle).
     sub = {k: v[20_000:20_512] for k, v in dev_text.items()}
     old = prod.trim_text
     try:
@@ -178,4 +182,6 @@ def _prompt_bank_checks(oracle, prod, text, dev_text, P):
         padded = prod.encode_text(sub)
     finally:
         prod.trim_text = old
-    assert torch.equal(padded, out[20_000:20_512])
+    rl_pad, _ = common.row_metrics(padded, out[20_000:20_512])
+    print(f"config 5: padded S=256 vs trimmed, 512 prompts: max rel-L2 {rl_pad:.2e}")
+    assert rl_pad <= 1e-3

@@ -198,7 +198,7 @@ def test_text_trimming_matches_padded_computation(tiny_pair):
     nomask_safe["attention_mask"] = text["attention_mask"].clone()
     nomask_safe["attention_mask"][0, -1] = 1  # forces s_eff = S; one extra attended PAD key in row 0 only
     padded = prod.encode_text(common.to_device(nomask_safe, DEV))
-    assert (trimmed[1:] - padded[1:]).abs().max().item() < 2e-4
+    assert (trimmed[1:] - padded[1:]).abs().max().item() < 2e-4  # S = 17 (packed tiles) vs S = 64 (one tile per prompt)
     with torch.no_grad():
         ref = oracle.encode_text(text)
     rl, cos = common.row_metrics(trimmed, ref)
@@ -232,8 +232,14 @@ def test_text_precision_modes(full_pair):
     assert rl_h <= HIGH_REL_TEXT and rl_f <= FAST_REL_TEXT and cos_f >= FP16_COS
     assert rl_h < 0.5 * rl_f                               # the split operands are what buys the accuracy
     assert torch.equal(res["auto"], res["high"])           # 12 prompts <= 8192: auto = high
-    one = prod.encode_text({k: v[5:6] for k, v in dtext.items()})   # batch-1 call, as the reference builds classifiers
-    assert (one - res["auto"][5:6]).abs().max().item() < 2e-5
+    # batch-1 calls, as the reference builds its classifiers (utils.py:67-74): a prompt alone (trimmed to its own length,
+    # alone in its attention tile) against its row of the batched call. Same arithmetic, but the keys sit at other tile
+    # offsets, so fp32 sums are taken in another order and a few of the 16-bit q/k/v/P roundings fall the other way:
+    # the embeddings agree to a few 1e-5 per element (measured 1.8e-5), an order of magnitude inside the parity gate.
+    for i in (0, 5, 11):
+        one = prod.encode_text({k: v[i:i + 1] for k, v in dtext.items()})
+        assert (one - res["auto"][i:i + 1]).abs().max().item() < 6e-5, i
+        assert common.row_metrics(one, res["auto"][i:i + 1])[0] < 2.5e-4, i
 
 
 def test_per_layer_parity_table(full_pair, golden_dir):
