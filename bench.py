@@ -164,6 +164,162 @@ def workload_name():
 
 
 # -------------------------------------------------------------------------------------------------------------
+# BASELINE configs 3 / 4 / 5 (the `extra` block of the GPU arm)
+# -------------------------------------------------------------------------------------------------------------
+def _synthetic_prompts(n, dev, seed):
+    """Tokenizer-shaped prompts: [CLS]=2 ... [SEP]=3, lengths U{4..32}, ids U{5..30521}, padded to 256."""
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(4, 33, (n,), generator=g)
+    ids = torch.randint(5, 30522, (n, 256), generator=g)
+    pos = torch.arange(256)[None, :]
+    ids = torch.where(pos < lens[:, None], ids, torch.zeros_like(ids))
+    ids[:, 0] = 2
+    ids[torch.arange(n), lens - 1] = 3
+    mask = (pos < lens[:, None]).long()
+    return {"input_ids": ids.to(dev), "token_type_ids": torch.zeros_like(ids).to(dev), "attention_mask": mask.to(dev)}
+
+
+def run_extras(args, model16, cfg16, dev, rank, world, timed):
+    """Returns the `extra` dict (rank 0) / None. Every timed region is device-timed, max over ranks, one warm-up pass of a
+    few batches first (kernels and tensor maps are warm from the headline)."""
+    from keep_b200 import KEEPConfig, KEEPModel, ops, wsi
+    from keep_b200 import distributed as kd
+    from keep_b200.weights import random_state_dict
+
+    sc = args.extra_scale
+    peaks = measured_peaks()
+    out = {}
+    POOL = 4096  # distinct resident synthetic tiles, cycled (2.5 GB fp32 >> 126 MB L2): every tile is encoded, none cached
+    g = torch.Generator(device=dev).manual_seed(1235 + rank)
+    pool = torch.empty(POOL, 3, 224, 224, dtype=torch.float32, device=dev)
+    for b0 in range(0, POOL, BATCH):
+        pool[b0:b0 + BATCH].normal_(generator=g)
+
+    def pool_tiles(lo, hi):  # tiles [lo, hi) of the slide
+        a = lo % POOL
+        if a + (hi - lo) <= POOL:
+            return pool[a:a + (hi - lo)]
+        return torch.cat([pool[a:], pool[:(hi - lo) - (POOL - a)]])
+
+    # ---- config 3: zeroshot_subtyping_WSI, 50,000 tiles strong-scaled, 256 prompt columns (64 classifiers x 4) ----
+    n3 = max(world, int(50_000 * sc))
+    text = _synthetic_prompts(256, dev, 3001)
+    coords3 = torch.stack(torch.meshgrid(torch.arange(224), torch.arange(224), indexing="ij"), -1).reshape(-1, 2)[:n3].to(dev) * 256
+    res3 = {}
+    for dtype_name in ("float16", "bfloat16"):
+        if dtype_name == "float16":
+            m = model16
+        else:
+            with torch.device(dev):
+                m = KEEPModel(KEEPConfig(operand_dtype="bfloat16"))
+            m.load_state_dict(random_state_dict(cfg16, seed=0, device=dev), strict=True)
+            m.eval()
+        bank = m.encode_text(text).t().contiguous()  # [768, 256]
+        classifier = bank[:, :4].contiguous()         # the slide-level head runs on one 4-class classifier
+        lo, hi = kd.shard_range(n3, rank, world)
+        result = {}
+
+        def step3():
+            feats = kd.encode_tiles_sharded(m, n3, pool_tiles, batch=BATCH, gather_dtype=torch.float16)  # one all-gather
+            ops.similarity(feats, bank, group=4, temp=10.0, want_logits=False, out_probs=probs3, workspace=ws3)
+            result["label"] = wsi.zero_shot_subtyping(classifier, feats, coords3, patch_size=256, overlap=True)
+
+        probs3 = torch.empty(n3, 256, dtype=torch.float32, device=dev)
+        ws3 = torch.empty(768 * 256 * 4, dtype=torch.uint8, device=dev)
+        m.encode_image(pool_tiles(0, min(BATCH, hi - lo) if hi > lo else 1))  # warm this handle
+        ms = timed(step3, 1)
+        res3[dtype_name] = {"ms": ms, "tiles_per_s": n3 / (ms / 1e3), "tiles_per_rank": hi - lo,
+                            "whole_path_frac": n3 / (ms / 1e3) * FLOP_PER_TILE / (world * peaks["tflops_sustained"] * 1e12),
+                            "slide_label": int(result["label"])}
+        if dtype_name == "bfloat16":
+            del m
+            torch.cuda.empty_cache()
+    out["config3_subtyping"] = {
+        "workload": f"{n3} tiles x 256 prompt columns (64 classifiers x 4), STRONG-scaled: {kd.shard_size(n3, world)} tiles per rank, "
+                    f"batches of {BATCH} (ragged last batch), fp16 all-gather of the [N,768] embeddings, similarity + softmax(x10) + "
+                    "refine + slide label inside the timed region",
+        "scaling": "strong", "n_gpus": world, **res3}
+
+    # ---- config 4: zeroshot_segmentation_WSI, 200,000 overlapping tiles streamed from pinned uint8 host batches ----
+    n4 = max(world, int(200_000 * sc))
+    lo, hi = kd.shard_range(n4, rank, world)
+    HPOOL = 8192  # pinned host pool of uint8 tiles (1.2 GB), cycled: every batch crosses PCIe inside the timed region
+    host_pool = torch.empty(HPOOL, 224, 224, 3, dtype=torch.uint8, pin_memory=True)
+    gh = torch.Generator().manual_seed(2000 + rank)
+    host_pool.view(-1)[:] = torch.randint(0, 256, (HPOOL * 224 * 224 * 3,), generator=gh, dtype=torch.uint8)
+    side = int(n4 ** 0.5) + 1
+    coords4 = torch.stack(torch.meshgrid(torch.arange(side), torch.arange(side), indexing="ij"), -1).reshape(-1, 2)[:n4].to(dev) * 112
+    cls2 = model16.encode_text({k: v[:2] for k, v in text.items()}).t().contiguous()  # [768, 2]
+    per = kd.shard_size(n4, world)
+    probs_local = torch.zeros(per, 2, dtype=torch.float32, device=dev)
+    stage = [torch.empty(BATCH, 224, 224, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    ws4 = torch.empty(768 * 2 * 4 + 64, dtype=torch.uint8, device=dev)
+    seg = {}
+
+    def step4():
+        main = torch.cuda.current_stream(dev)
+        for i, b0 in enumerate(range(lo, hi, BATCH)):
+            n = min(BATCH, hi - b0)
+            s_ = i & 1
+            a = b0 % HPOOL
+            n_first = min(n, HPOOL - a)
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(freed[s_])
+                stage[s_][:n_first].copy_(host_pool[a:a + n_first], non_blocking=True)
+                if n_first < n:
+                    stage[s_][n_first:n].copy_(host_pool[:n - n_first], non_blocking=True)
+                ready[s_].record(copy_stream)
+            main.wait_event(ready[s_])
+            feats = model16.encode_image(stage[s_][:n])  # uint8 NHWC: ToTensor + Normalize fused into the patch gather
+            freed[s_].record(main)
+            ops.similarity(feats, cls2, group=2, temp=10.0, want_logits=False, out_probs=probs_local[b0 - lo:b0 - lo + n],
+                           workspace=ws4)
+        probs_all = kd.all_gather_rows(probs_local[:hi - lo], n4)  # [n4, 2] on every rank: the path's one collective
+        if rank == 0:
+            idx, _, refined = wsi.refine_tensors(probs_all, coords4, 224, True)  # refine_seg over the whole slide
+            seg["tumour_fraction"] = float((refined[:, 1] > 0.5).float().mean().item())  # result read back on the host
+        main.synchronize()
+
+    ms4 = timed(step4, 1)
+    out["config4_segmentation"] = {
+        "workload": f"{n4} overlapping tiles (stride 112) x 2 prompt columns, {per} tiles per rank streamed from PINNED uint8 host "
+                    f"batches of {BATCH} (double-buffered H2D inside the timed region), probabilities all-gathered, refine_seg on rank 0",
+        "scaling": "strong", "n_gpus": world, "ms": ms4, "tiles_per_s": n4 / (ms4 / 1e3),
+        "h2d_bytes": int((hi - lo) * 224 * 224 * 3), "tumour_fraction": seg.get("tumour_fraction"),
+        "whole_path_frac": n4 / (ms4 / 1e3) * FLOP_PER_TILE / (world * peaks["tflops_sustained"] * 1e12)}
+    del host_pool, stage, pool
+    torch.cuda.empty_cache()
+
+    # ---- config 5 (single GPU): the 91,632-prompt bank at seq_len 256, padded and trimmed ----
+    if world == 1:
+        n5 = max(1, int(91_632 * sc))
+        bank_text = _synthetic_prompts(n5, dev, 3000)
+        res5 = {}
+        for mode in ("padded", "trimmed"):
+            model16.trim_text = mode == "trimmed"
+            sub = {k: v[:2048] for k, v in bank_text.items()}
+            model16.encode_text(sub)  # warm the shapes of this mode
+
+            def step5():
+                for p0 in range(0, n5, 16384):
+                    model16.encode_text({k: v[p0:p0 + 16384] for k, v in bank_text.items()})
+
+            ms5 = timed(step5, 1)
+            res5[mode] = {"ms": ms5, "prompts_per_s": n5 / (ms5 / 1e3)}
+        model16.trim_text = True
+        res5["padded"]["bert_roofline_frac"] = res5["padded"]["prompts_per_s"] * FLOP_PER_PROMPT_PADDED / (peaks["tflops_sustained"] * 1e12)
+        out["config5_prompt_bank"] = {
+            "workload": f"{n5} prompts (11,454 names x 8 templates), seq_len 256, lengths U{{4..32}}, calls of 16,384 prompts "
+                        "(text_precision auto -> one-pass GEMMs above 8,192 prompts per call)",
+            "flop_per_padded_prompt": FLOP_PER_PROMPT_PADDED, **res5}
+    return out if rank == 0 else None
+
+
+# -------------------------------------------------------------------------------------------------------------
 # GPU arm
 # -------------------------------------------------------------------------------------------------------------
 _REAL_STDOUT = None
@@ -247,11 +403,13 @@ def main():
 
     probs_out = torch.empty(n_tiles, N_PROMPTS, dtype=torch.float32, device=dev)
 
+    sim_ws = torch.empty(768 * 256 * 4, dtype=torch.uint8, device=dev)  # K-major classifier copy of the similarity kernel
+
     def step_resident():
         for b0 in range(0, n_tiles, BATCH):
             feats = model.encode_image(tiles[b0:b0 + BATCH])
-            _, pr = ops.similarity(feats, classifier, group=2, temp=10.0)
-            probs_out[b0:b0 + BATCH] = pr
+            ops.similarity(feats, classifier, group=2, temp=10.0, want_logits=False, out_probs=probs_out[b0:b0 + BATCH],
+                           workspace=sim_ws)  # the task heads read probabilities only
         return _gather(probs_out) if world > 1 else probs_out
 
     gather_buf = torch.empty(world * n_tiles, N_PROMPTS, dtype=torch.float32, device=dev) if world > 1 else None
@@ -318,9 +476,9 @@ def main():
                     ready[s].record(copy_stream)
                 main.wait_event(ready[s])
                 feats = model.encode_image(stage[s][:n])
-                _, pr = ops.similarity(feats, classifier, group=2, temp=10.0)
                 freed[s].record(main)
-                probs_out[b0:b0 + n] = pr
+                ops.similarity(feats, classifier, group=2, temp=10.0, want_logits=False, out_probs=probs_out[b0:b0 + n],
+                               workspace=sim_ws)
             res = _gather(probs_out) if world > 1 else probs_out
             host_probs.copy_(res[rank * n_tiles:(rank + 1) * n_tiles] if world > 1 else res, non_blocking=True)
             main.synchronize()  # the caller holds the step's result on the host
@@ -332,10 +490,18 @@ def main():
                "api": "KEEPModel.encode_image + ops.similarity on pinned-host fp32 tiles, double-buffered H2D"}
         del host_tiles, stage
 
+    # ---- the other BASELINE configs, same run ----
+    extra = None
+    if not args.no_extras:
+        del tiles
+        tiles = None
+        torch.cuda.empty_cache()
+        extra = run_extras(args, model, cfg, dev, rank, world, timed)
+
     # ---- CPU baseline beside it (rank 0, single-GPU run only) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        del tiles
+        tiles = None
         torch.cuda.empty_cache()
         tps, ms_cpu, threads, cpu = cpu_reference_tiles_per_s(32, steps=2, warmup=1)
         cpu_baseline = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
@@ -368,6 +534,8 @@ def main():
         }
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
+        if extra:
+            line["extra"] = extra
         emit(line)
     if world > 1:
         torch.distributed.barrier()

@@ -162,7 +162,9 @@ int keepb200_encode_text(void* handle, const int64_t* ids, const int64_t* type_i
 /* logits[N,P] = normalize(feats)[N,D] @ cls[D,P];  probs[N,P] = softmax(temp * logits) over each
  * consecutive group of `group` columns (0 = one group of all P columns, the reference's single
  * classifier [D,C]; K stacked classifiers of C classes use group = C). feats and cls are fp32, cls in the
- * reference's [D,P] layout (utils.py:83). logits is required, probs may be NULL. D % 4 == 0.
+ * reference's [D,P] layout (utils.py:83). Either output may be NULL (probs alone: group must divide 16 and the
+ * tensor-core path be usable - the task heads only ever read the probabilities, and the kernel is HBM-bound on its
+ * outputs). D % 4 == 0.
  * workspace: P*D*4 bytes (keepb200_similarity_workspace_bytes) for the K-major copy of the classifier used by
  * the TF32 tcgen05 kernel (D % 32 == 0); with workspace == NULL the fp32 FMA kernel runs instead. */
 int keepb200_similarity(const float* feats, int64_t N, int64_t D, const float* cls, int64_t P, int group,

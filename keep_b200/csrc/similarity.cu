@@ -130,7 +130,7 @@ int launch_similarity(const float* feats, int64_t N, int D, const float* cls, in
                       float* logits, float* probs, cudaStream_t stream, float* clsT_scratch) {
   if (N <= 0 || P <= 0) return KB_OK;
   if (D % 4 != 0) return set_error(KB_ERR_ARG, "similarity: D=%d must be a multiple of 4", D);
-  if (logits == nullptr) return set_error(KB_ERR_ARG, "similarity: logits buffer is required");
+  if (logits == nullptr && probs == nullptr) return set_error(KB_ERR_ARG, "similarity: neither logits nor probs requested");
   if (group <= 0) group = P;
   if (P % group != 0) return set_error(KB_ERR_ARG, "similarity: P=%d is not a multiple of group=%d", P, group);
   if (clsT_scratch != nullptr && D % 32 == 0 && (reinterpret_cast<uintptr_t>(feats) & 15) == 0) {
@@ -141,6 +141,8 @@ int launch_similarity(const float* feats, int64_t N, int D, const float* cls, in
     rc = launch_similarity_tc(feats, N, D, clsT_scratch, P, group, temp, logits, probs, &fused, stream);
     if (rc) return rc;
     if (probs != nullptr && !fused) {
+      if (logits == nullptr)
+        return set_error(KB_ERR_ARG, "similarity: probabilities without logits need a group size dividing 16 (got %d)", group);
       const long long n = N * (P / group);
       group_softmax_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(logits, N, P, group, temp, probs);
       note_launch();
@@ -148,6 +150,7 @@ int launch_similarity(const float* feats, int64_t N, int D, const float* cls, in
     }
     return KB_OK;
   }
+  if (logits == nullptr) return set_error(KB_ERR_ARG, "similarity: the fp32 FMA path needs the logits buffer");
   dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)((P + BN - 1) / BN));
   sim_gemm_kernel<<<grid, 256, 0, stream>>>(feats, N, D, cls, P, logits);
   note_launch();

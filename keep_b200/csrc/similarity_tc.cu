@@ -314,6 +314,8 @@ int launch_similarity_tc(const float* feats, int64_t N, int D, const float* clsT
   p.logits = logits; p.probs = probs; p.score_part = score_part;
   p.idesc = make_idesc(kFmtTF32, SBM, BN);
   *fused_probs = probs != nullptr && (16 % group) == 0;
+  if (logits == nullptr && probs != nullptr && !*fused_probs)
+    return set_error(KB_ERR_ARG, "similarity_tc: probabilities without logits need a group size dividing 16 (got %d)", group);
   if (probs != nullptr && !*fused_probs) p.probs = nullptr;
   const long long tiles = ((N + SBM - 1) / SBM) * ((P + BN - 1) / BN);
   int grid = num_sms();

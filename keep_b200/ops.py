@@ -235,23 +235,30 @@ def act_l2norm(x, act=0):
     return y
 
 
-def similarity(feats, cls, group=0, temp=10.0, want_probs=True, tensor_cores=True):
+def similarity(feats, cls, group=0, temp=10.0, want_probs=True, tensor_cores=True, want_logits=True, out_logits=None,
+               out_probs=None, workspace=None):
     """logits = normalize(feats) @ cls ; probs = softmax(temp*logits) per `group` columns (0 = all).
-    tensor_cores=True: TF32 tcgen05 kernel (needs D % 32 == 0); False: fp32 FMA kernel (bit-closer to fp32)."""
+    tensor_cores=True: TF32 tcgen05 kernel (needs D % 32 == 0); False: fp32 FMA kernel (bit-closer to fp32).
+    out_logits / out_probs: preallocated [N, P] fp32 row blocks to write into (e.g. slices of a slide-sized buffer);
+    want_logits=False skips the logits (group must divide 16): the kernel is bound by its output bytes."""
     _need_cuda(feats, cls)
     feats = feats.contiguous().float()
     cls = cls.contiguous().float()
     N, D = feats.shape
     P = cls.shape[1]
     assert cls.shape[0] == D
-    logits = torch.empty(N, P, dtype=torch.float32, device=feats.device)
-    probs = torch.empty(N, P, dtype=torch.float32, device=feats.device) if want_probs else None
+    for o in (out_logits, out_probs):
+        assert o is None or (o.shape == (N, P) and o.dtype == torch.float32 and o.is_contiguous() and o.device == feats.device)
+    logits = out_logits if out_logits is not None else (torch.empty(N, P, dtype=torch.float32, device=feats.device) if want_logits else None)
+    probs = out_probs if out_probs is not None else (torch.empty(N, P, dtype=torch.float32, device=feats.device) if want_probs else None)
     L = _lib.lib()
     ws_bytes = L.keepb200_similarity_workspace_bytes(D, P) if tensor_cores else 0
-    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=feats.device) if tensor_cores else None
+    ws = None
+    if tensor_cores:
+        ws = workspace if workspace is not None and workspace.numel() >= ws_bytes else torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=feats.device)
     with _on(feats):
         _lib.check(
-            L.keepb200_similarity(feats.data_ptr(), N, D, cls.data_ptr(), P, group, temp, logits.data_ptr(), _lib.ptr(probs),
+            L.keepb200_similarity(feats.data_ptr(), N, D, cls.data_ptr(), P, group, temp, _lib.ptr(logits), _lib.ptr(probs),
                                   _lib.ptr(ws), ws_bytes, _lib.stream_ptr(feats.device)),
             "similarity",
         )

@@ -154,7 +154,10 @@ def tile_probabilities(classifier: torch.Tensor, tile_features: torch.Tensor, mo
 # ---------------------------------------------------------------------------------------------------------
 def refine_tensors(probs: torch.Tensor, tile_coords, patch_size: int, overlap: bool):
     """(kept index [M], coords [M,2] int64, refined probs [M,C]) in first-occurrence order, on the device."""
-    coords = torch.as_tensor(np.asarray(tile_coords)).to(device=probs.device, dtype=torch.long).reshape(-1, 2)
+    if isinstance(tile_coords, torch.Tensor):  # the reference passes the h5 `coords` array; device tensors are taken as they are
+        coords = tile_coords.to(device=probs.device, dtype=torch.long).reshape(-1, 2)
+    else:
+        coords = torch.as_tensor(np.asarray(tile_coords)).to(device=probs.device, dtype=torch.long).reshape(-1, 2)
     keep, refined = ops.refine(coords, probs, patch_size, overlap)
     idx = keep.nonzero().flatten()
     return idx, coords[idx], refined[idx]
