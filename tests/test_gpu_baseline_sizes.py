@@ -185,3 +185,44 @@ def _prompt_bank_checks(oracle, prod, text, dev_text, P):
     rl_pad, _ = common.row_metrics(padded, out[20_000:20_512])
     print(f"config 5: padded S=256 vs trimmed, 512 prompts: max rel-L2 {rl_pad:.2e}")
     assert rl_pad <= 1e-3
+
+
+@pytest.mark.parametrize("operand_dtype", ["float16", "bfloat16"])
+def test_config3_config4_tile_tower_on_a_ragged_shard(full_pair, operand_dtype):
+    """BASELINE configs 3 / 4 through the TILE TOWER (not random features): a 1,130-tile shard = two 512-tile workspace
+    chunks + a ragged 106-tile one, fed as batches of 1024 + 106 exactly as bench.py's extras do (fp32 tiles for config 3,
+    uint8 NHWC for config 4), 256 prompt columns / 2 prompt columns; a sample of the rows against the fp32 oracle."""
+    from keep_b200 import distributed as kd
+    from keep_b200 import ops
+
+    oracle, prod16 = full_pair
+    if operand_dtype == "float16":
+        prod, gate = prod16, 1.25e-3
+    else:
+        prod, gate = common.full_product(common.full_oracle(seed=0)[1], operand_dtype="bfloat16"), 2e-2
+    N = 1130
+    g = torch.Generator(device=DEV).manual_seed(1235)
+    tiles = torch.randn(N, 3, 224, 224, device=DEV, generator=g)
+    feats = kd.encode_tiles_sharded(prod, N, lambda lo, hi: tiles[lo:hi], batch=1024, gather_dtype=torch.float16)
+    assert feats.shape == (N, 768) and torch.isfinite(feats).all()
+    idx = torch.tensor([0, 511, 512, 1023, 1024, 1129])  # chunk and batch boundaries, the ragged tail
+    with torch.no_grad():
+        ref = oracle.encode_image(tiles[idx].cpu())
+    rl, cos = common.row_metrics(feats[idx], ref)
+    print(f"ragged shard, {operand_dtype}: rel-L2 {rl:.2e} (embeddings gathered as fp16)")
+    assert rl <= gate and cos >= (0.99999 if operand_dtype == "float16" else 0.9995)
+    cls = F.normalize(torch.randn(768, 256, device=DEV, generator=g), dim=0)
+    _, probs = ops.similarity(feats, cls, group=4, temp=10.0, want_logits=False)
+    ref_p = torch.softmax((F.normalize(ref, dim=-1) @ cls.cpu()).view(len(idx), 64, 4) * 10, -1).view(len(idx), 256)
+    assert (probs[idx].cpu() - ref_p).abs().max().item() <= (5e-3 if operand_dtype == "float16" else 5e-2)
+    assert (probs.view(N, 64, 4).sum(-1) - 1).abs().max().item() < 1e-5
+    if operand_dtype == "float16":  # config 4: the same shard as raw uint8 tiles with the normalisation fused into the patch gather
+        u8 = torch.randint(0, 256, (N, 224, 224, 3), device=DEV, generator=g, dtype=torch.uint8)
+        f8 = torch.cat([prod.encode_image(u8[b0:b0 + 1024]) for b0 in range(0, N, 1024)])
+        mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+        std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+        with torch.no_grad():
+            ref8 = oracle.encode_image((u8[idx].cpu().permute(0, 3, 1, 2).float() / 255.0 - mean) / std)
+        rl8, cos8 = common.row_metrics(f8[idx], ref8)
+        print(f"ragged shard, uint8 tiles: rel-L2 {rl8:.2e}")
+        assert rl8 <= gate and cos8 >= 0.99999

@@ -127,3 +127,48 @@ def test_chunked_pinned_upload_matches_source():
     assert torch.equal(kio.to_device(feats, "cuda:0", chunk_rows=1024).cpu(), feats)
     assert torch.equal(kio.to_device(coords, "cuda:0", chunk_rows=4096).cpu(), coords)
     assert kio.to_device(feats[:0], "cuda:0").shape == (0, 768)
+
+
+@pytest.mark.parametrize("task", ["detection", "subtyping", "segmentation"])
+def test_slide_level_flow_matches_the_reference_flow(task):
+    """The whole script flow (prompt file -> K classifiers -> screening -> top-n ensemble -> task head,
+    zeroshot_*_WSI.py:26-71) through keep_b200.slide on the device against the reference's flow on the CPU oracle
+    (batch-1 encode_text per class, one GEMM + topk per classifier, Python dict walk)."""
+    from keep_b200.slide import TASK_DEFAULTS, zero_shot_slide
+
+    oracle, sd, text_cfg = common.tiny_oracle(seed=4, max_pos=256)
+    prod = common.tiny_product(sd, text_cfg)
+    tok = FakeTokenizer(1000)
+    d = TASK_DEFAULTS[task]
+    classes = ["CCRCC", "PRCC", "CHRCC", "Normal"] if task == "subtyping" else ["Normal", "Tumor"]
+    words = ["clear", "cell", "papillary", "renal", "tumor", "tissue", "normal", "dense", "stroma", "necrotic", "benign", "chromophobe"]
+    rng = np.random.default_rng(11)
+    K = 48
+    prompts = {str(i): {"classnames": {c: " ".join(words[j] for j in rng.integers(0, len(words), int(rng.integers(2, 5))))
+                                       for c in classes}, "templates": "CLASSNAME."} for i in range(K)}
+    g = torch.Generator().manual_seed(31)
+    N = 2500
+    feats = torch.randn(N, 128, generator=g)
+    side = 50
+    coords = np.stack([(np.arange(N) % side) * d["patch_size"], (np.arange(N) // side) * d["patch_size"]], 1)
+    coords[-40:] = coords[:40]  # duplicates: first tile wins
+    timings = {}
+    got = zero_shot_slide(task, {"model": prod, "tokenizer": tok}, prompts, feats.to(DEV), coords, DEV, topn=7, timings=timings)
+    assert timings["classifiers"] == K and timings["tiles"] == N and timings["classifier_bank_s"] > 0
+    # the reference flow
+    bank = [wo.get_zeroshot_classifier(oracle, tok, d["label_map"], prompts[str(i)], "cpu", add_normal=d["add_normal"]) for i in range(K)]
+    ens, scores = wo.zero_shot_prompt_select(bank, feats, topn=7)
+    if task == "detection":
+        exp = wo.zero_shot_detection(ens, feats, coords, patch_size=d["patch_size"], overlap=d["overlap"])
+        assert got == pytest.approx(float(exp), abs=3 / N)          # a handful of tiles sit within 1e-3 of the 0.5 threshold
+    elif task == "subtyping":
+        exp = wo.zero_shot_subtyping(ens, feats, coords, patch_size=d["patch_size"], overlap=d["overlap"])
+        assert int(got) == int(exp)
+    else:
+        _, probs = wo.tile_probs(ens, feats)
+        exp = wo.refine_seg_segment(probs.numpy(), coords, patch_size=d["patch_size"], overlap=d["overlap"])
+        assert list(got.keys()) == list(exp.keys())                  # same kept tiles, same (first-occurrence) order
+        assert np.abs(np.array(list(got.values())) - np.array(list(exp.values()))).max() < 2e-3
+    # ... and without screening the ensemble is the scripts' seeded random draw
+    got2 = zero_shot_slide(task, {"model": prod, "tokenizer": tok}, prompts, feats.to(DEV), coords, DEV, topn=7, prompt_screening=False)
+    assert type(got2) is type(got)
