@@ -35,7 +35,8 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// acc[j][r] = sum_k in[r][k] * wt[k, tid + 256 j]
+// acc[j][r] = sum_k in[r][k] * wt[k, tid + 256 j]. The weight rows of the NEXT four k are requested before the FMAs of the
+// current four run (register double buffer): with 8 warps per SM and ~300 cycles to L2 the loop is otherwise latency-bound.
 template <int R>
 __device__ __forceinline__ void linear_rows(const float* __restrict__ wt, int K, int N, const float* in, int in_ld,
                                             float (&acc)[kMaxCols][R]) {
@@ -44,14 +45,18 @@ __device__ __forceinline__ void linear_rows(const float* __restrict__ wt, int K,
 #pragma unroll
     for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
   const int tid = threadIdx.x;
-  for (int k = 0; k < K; k += 4) {
-    float w[kMaxCols][4];
+  float w[kMaxCols][4], wn[kMaxCols][4];
+  auto load = [&](float (&dst)[kMaxCols][4], int k) {
 #pragma unroll
     for (int j = 0; j < kMaxCols; ++j) {
       const int c = tid + kHeadThreads * j;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) w[j][i] = c < N ? __ldg(wt + (long long)(k + i) * N + c) : 0.f;
+      for (int i = 0; i < 4; ++i) dst[j][i] = (c < N && k + i < K) ? __ldg(wt + (long long)(k + i) * N + c) : 0.f;
     }
+  };
+  load(w, 0);
+  for (int k = 0; k < K; k += 4) {
+    load(wn, k + 4);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const float4 xv = *reinterpret_cast<const float4*>(in + r * in_ld + k);  // same address in every thread: broadcast
@@ -63,6 +68,10 @@ __device__ __forceinline__ void linear_rows(const float* __restrict__ wt, int K,
         acc[j][r] = fmaf(xv.w, w[j][3], acc[j][r]);
       }
     }
+#pragma unroll
+    for (int j = 0; j < kMaxCols; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[j][i] = wn[j][i];
   }
 }
 

@@ -16,16 +16,7 @@ cfg = KEEPConfig()
 with torch.device(dev):
     model = KEEPModel(cfg)
 model.load_state_dict(random_state_dict(cfg, seed=0, device=dev), strict=True)
-g = torch.Generator().manual_seed(0)
-P = 512
-lens = torch.randint(4, 33, (P,), generator=g)
-ids = torch.randint(5, 30522, (P, 256), generator=g)
-mask = (torch.arange(256)[None, :] < lens[:, None]).long()
-text = {"input_ids": (ids * mask).to(dev), "token_type_ids": torch.zeros_like(ids).to(dev), "attention_mask": mask.to(dev)}
-emb = model.encode_text(text)                      # trimmed, high precision
-model.trim_text = False
-model.config.text_precision = "fast"
-emb_padded = model.encode_text(text)               # padded S = 256, one-pass GEMMs
+# WSI kernels first, then the text tower: ncu captures the first N matching launches
 gd = torch.Generator(device=dev).manual_seed(1)
 feats = torch.randn(50_000, 768, device=dev, generator=gd)
 cls = torch.nn.functional.normalize(torch.randn(768, 256, device=dev, generator=gd), dim=0)
@@ -39,5 +30,15 @@ side = 448
 coords = torch.stack(torch.meshgrid(torch.arange(side), torch.arange(side), indexing="ij"), -1).reshape(-1, 2)[:200_000].to(dev) * 112
 ops.refine(coords, p2, 224, True)
 preprocess(torch.randint(0, 256, (256, 256, 256, 3), device=dev, dtype=torch.uint8, generator=gd))
+g = torch.Generator().manual_seed(0)
+P = 512
+lens = torch.randint(4, 33, (P,), generator=g)
+ids = torch.randint(5, 30522, (P, 256), generator=g)
+mask = (torch.arange(256)[None, :] < lens[:, None]).long()
+text = {"input_ids": (ids * mask).to(dev), "token_type_ids": torch.zeros_like(ids).to(dev), "attention_mask": mask.to(dev)}
+emb = model.encode_text(text)                      # trimmed, high precision
+model.trim_text = False
+model.config.text_precision = "fast"
+emb_padded = model.encode_text(text)               # padded S = 256, one-pass GEMMs
 torch.cuda.synchronize()
 print("ok", float(emb.sum()), float(emb_padded.sum()))
