@@ -357,6 +357,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE configs 3/4/5 block")
     ap.add_argument("--extra-scale", type=float, default=1.0, help="scale the tile/prompt counts of the extras (tests)")
+    ap.add_argument("--ln-fuse", type=int, default=None, choices=[0, 1, 2],
+                    help="A/B hook (keepb200_debug_set_ln_fuse): which LayerNorms are folded into the next GEMM; default = the library's")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "keep_b200" else max(args.warmup, 1)
 
@@ -384,6 +386,8 @@ def main():
         model = KEEPModel(cfg)
     model.load_state_dict(random_state_dict(cfg, seed=0, device=dev), strict=True)
     model.eval()
+    if args.ln_fuse is not None:
+        model.debug_set_ln_fuse(args.ln_fuse)
 
     # ---- inputs: tiles resident in HBM (6.0 GB > 126 MB L2), 32 prompts -> 16 two-class classifiers ----
     g = torch.Generator(device=dev).manual_seed(1234 + rank)

@@ -92,9 +92,11 @@ enum { EV_S_ISSUE = 0, EV_PV_WAITED = 1, EV_PV_ISSUED = 2, EV_SM_START = 3, EV_S
       p.trace[(u) * 16 + (ev)] = clock64();                                                      \
   } while (0)
 
+template <bool BF16>
 __global__ void __launch_bounds__(kAtcThreads, 1)
 attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     const Atc1Params p) {
+  constexpr int kBf = BF16 ? 1 : 0;  // compile-time 16-bit format: one F2FP per pair in the softmax, no predicated twin
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* s_bias = reinterpret_cast<float*>(smem + Smem::bias);
@@ -260,7 +262,7 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           const float f = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);  // exact power of two, or 1
           sum *= f;
           uint32_t f2;
-          if (p.bf16) {
+          if (kBf) {
             __nv_bfloat162 h = __floats2bfloat162_rn(f, f);
             f2 = *reinterpret_cast<uint32_t*>(&h);
           } else {
@@ -274,7 +276,7 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              if (p.bf16) {
+              if (kBf) {
                 __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&w[i]), *reinterpret_cast<__nv_bfloat162*>(&f2));
                 w[i] = *reinterpret_cast<uint32_t*>(&r);
               } else {
@@ -301,15 +303,17 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const float neg_m = -m_ref;
         float s0 = 0.f, s1 = 0.f;
         uint32_t pk[16];
-#pragma unroll
         const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(neg_m, neg_m), one2 = make_float2(1.f, 1.f);
         float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll
         for (int i = 0; i < 16; ++i) {
           // packed fp32 (FFMA2): the scale-and-shift and the running sums of two keys per instruction
           const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sc2, nm2);
+          // (exp2 of part of the pairs from an FMA-pipe polynomial, FlashAttention-4 style, was measured here: 246 us with
+          // none, 248 us with 2 of 8 pairs, 272 us with 3 of 8 - tools/microbench/softmax_exp_mix.cu)
           const float2 e = make_float2(ex2f(t.x), ex2f(t.y));
           acc2 = __ffma2_rn(e, one2, acc2);
-          pk[i] = pack16(e.x, e.y, p.bf16);
+          pk[i] = pack16(e.x, e.y, kBf);
         }
         s0 += acc2.x;
         s1 += acc2.y;
@@ -358,9 +362,9 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float e0 = ex2f(t[2 * i] + neg_m), e1 = ex2f(t[2 * i + 1] + neg_m);
-          pk[i] = pack16(e0, e1, p.bf16);
+          pk[i] = pack16(e0, e1, kBf);
           if (p.key_mask != nullptr) {  // masked (text) rows: sum the ROUNDED probabilities, as attention_tc.cu does
-            const float2 r = unpack16(pk[i], p.bf16);
+            const float2 r = unpack16(pk[i], kBf);
             sum += r.x + r.y;
           } else {
             sum += e0 + e1;
@@ -418,18 +422,18 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(half == 0 ? va[i + e] : vb[i + e]) * inv;
             uint4 w;
-            w.x = pack16(f[0], f[1], p.bf16);
-            w.y = pack16(f[2], f[3], p.bf16);
-            w.z = pack16(f[4], f[5], p.bf16);
-            w.w = pack16(f[6], f[7], p.bf16);
+            w.x = pack16(f[0], f[1], kBf);
+            w.y = pack16(f[2], f[3], kBf);
+            w.z = pack16(f[4], f[5], kBf);
+            w.w = pack16(f[6], f[7], kBf);
             *reinterpret_cast<uint4*>(orow + 32 * half + i) = w;
             if (p.lo_off > 0) {  // rounding remainder of the context: the output projection then runs split-operand
-              const float2 h0 = unpack16(w.x, p.bf16), h1 = unpack16(w.y, p.bf16), h2 = unpack16(w.z, p.bf16), h3 = unpack16(w.w, p.bf16);
+              const float2 h0 = unpack16(w.x, kBf), h1 = unpack16(w.y, kBf), h2 = unpack16(w.z, kBf), h3 = unpack16(w.w, kBf);
               uint4 l;
-              l.x = pack16(f[0] - h0.x, f[1] - h0.y, p.bf16);
-              l.y = pack16(f[2] - h1.x, f[3] - h1.y, p.bf16);
-              l.z = pack16(f[4] - h2.x, f[5] - h2.y, p.bf16);
-              l.w = pack16(f[6] - h3.x, f[7] - h3.y, p.bf16);
+              l.x = pack16(f[0] - h0.x, f[1] - h0.y, kBf);
+              l.y = pack16(f[2] - h1.x, f[3] - h1.y, kBf);
+              l.z = pack16(f[4] - h2.x, f[5] - h2.y, kBf);
+              l.w = pack16(f[6] - h3.x, f[7] - h3.y, kBf);
               *reinterpret_cast<uint4*>(orow + p.lo_off + 32 * half + i) = l;
             }
           }
@@ -463,7 +467,8 @@ int launch_attention_tc1(const void* qkv, void* out, int B, int S, int H, int bf
   rc = get_tmap_2d(qkv, dt, rows, cols, cols, S_pad, &tkv);
   if (rc) return rc;
   const int smem = Smem::total + 1024;
-  KB_TRY_ATTR(attention_tc1_kernel, smem);
+  KB_TRY_ATTR(attention_tc1_kernel<true>, smem);
+  KB_TRY_ATTR(attention_tc1_kernel<false>, smem);
   Atc1Params p;
   p.B = B; p.S = S; p.H = H; p.S_pad = S_pad; p.n_qt = (S + 127) / 128; p.items = B * H;
   p.key_mask = reinterpret_cast<const long long*>(key_mask);
@@ -478,7 +483,8 @@ int launch_attention_tc1(const void* qkv, void* out, int B, int S, int H, int bf
   p.trace = trace;
   int grid = num_sms();
   if (p.items < grid) grid = p.items;
-  attention_tc1_kernel<<<grid, kAtcThreads, smem, stream>>>(tq, tkv, p);
+  if (bf16) attention_tc1_kernel<true><<<grid, kAtcThreads, smem, stream>>>(tq, tkv, p);
+  else attention_tc1_kernel<false><<<grid, kAtcThreads, smem, stream>>>(tq, tkv, p);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;

@@ -97,6 +97,29 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   return __ffma2_rn(make_float2(-ax.x, -ax.y), e, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
 }
 
+// Two independent pairs step by step (four elements of a row): the dependent FFMA2 chain of one pair fills the
+// issue slots the other one waits in — the epilogue warps are only two per SM sub-partition.
+template <int DEG>
+__device__ __forceinline__ void gelu_erf2x2(float2& x0, float2& x1) {
+  static_assert(DEG == 4, "interleaved form is written for the degree-4 polynomial");
+  const float2 a0 = make_float2(fabsf(x0.x), fabsf(x0.y)), a1 = make_float2(fabsf(x1.x), fabsf(x1.y));
+  const float2 m0 = make_float2(fminf(a0.x, 6.0f), fminf(a0.y, 6.0f)), m1 = make_float2(fminf(a1.x, 6.0f), fminf(a1.y, 6.0f));
+  const float2 k4 = make_float2(3.920550193e-03f, 3.920550193e-03f), k3 = make_float2(-4.439129536e-02f, -4.439129536e-02f);
+  const float2 k2 = make_float2(-4.674139173e-01f, -4.674139173e-01f), k1 = make_float2(-1.147820817e+00f, -1.147820817e+00f);
+  const float2 k0 = make_float2(-1.000374045e+00f, -1.000374045e+00f);
+  float2 p0 = __ffma2_rn(m0, k4, k3), p1 = __ffma2_rn(m1, k4, k3);
+  p0 = __ffma2_rn(m0, p0, k2); p1 = __ffma2_rn(m1, p1, k2);
+  p0 = __ffma2_rn(m0, p0, k1); p1 = __ffma2_rn(m1, p1, k1);
+  p0 = __ffma2_rn(m0, p0, k0); p1 = __ffma2_rn(m1, p1, k0);
+  float2 e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0.x) : "f"(p0.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1.x) : "f"(p1.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0.y) : "f"(p0.y));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1.y) : "f"(p1.y));
+  x0 = __ffma2_rn(make_float2(-a0.x, -a0.y), e0, make_float2(fmaxf(x0.x, 0.0f), fmaxf(x0.y, 0.0f)));
+  x1 = __ffma2_rn(make_float2(-a1.x, -a1.y), e1, make_float2(fmaxf(x1.x, 0.0f), fmaxf(x1.y, 0.0f)));
+}
+
 __device__ __forceinline__ uint32_t pack16(float a, float b, int bf16) {
   if (bf16) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -124,17 +147,32 @@ template <int EPI> struct EpiTraits {
 // accumulator at `tmem_acc`; rows row0.. of the output, tile column base n0. The warp waits for the accumulator
 // (`tfull`, `parity`) itself, AFTER it has issued the global loads that do not depend on it (bias, LayerScale, the
 // first residual block, the LayerNorm statistics of its rows), so their DRAM latency hides behind the wait.
-template <int EPI>
+//
+// BF16 (16-bit output format) and FULL (all 32 rows of this warp lie inside M: no per-row guards, so the eight row groups
+// of a block are one basic block the compiler can interleave) are compile-time: the instruction count of the epilogue is
+// what paces the GEMMs with short K (profiles/r02_src_gemm notes in DESIGN.md), so nothing is re-decided per element.
+template <int EPI, bool BF16, bool FULL_ROWS>
 __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_acc, int q, int lane, int row0, int n0,
                                               int c_begin, int c_end, uint8_t* stage, uint64_t* tfull, uint32_t parity,
                                               int tag) {
   using T = EpiTraits<EPI>;
+  constexpr int kBf = BF16 ? 1 : 0;
+  // the residual epilogues keep their row guards even on full tiles: without them ptxas hoists the address arithmetic of
+  // all eight row groups of three arrays and spills (measured: fc2 1,209 -> 1,165 TFLOP/s in the step)
+  constexpr bool FULL = FULL_ROWS && !T::kResid;
   const uint32_t stage_addr = smem_u32(stage);
   // transposed role of this lane: rows 4i + (lane >> 3), columns 4*(lane & 7) .. +3 of the 32x32 block
   const int tr = lane >> 3, tc = (lane & 7) * 4;
   const uint32_t t_lane = tmem_acc + (uint32_t(q * 32) << 16);
   int c_stop = c_end;
   if (n0 + c_stop > p.N) c_stop = p.N - n0;  // N is a multiple of 32 (warp-uniform)
+  // element pointers of this lane's first row (row0 + tr) at column tc, and the distance between its row groups (4 rows):
+  // a block adds its column, a row group i adds i * step, nothing else is recomputed per element
+  // (the 16-bit-output epilogues only: the residual epilogues already hold two residual blocks in registers and
+  // recompute their addresses from the row index instead of keeping 8 row pointers per array alive)
+  const long long first = row0 + tr;
+  uint16_t* out16_base = T::kHalfOut ? reinterpret_cast<uint16_t*>(p.out) + first * p.ldo + tc : nullptr;
+  const long long out16_step = 4 * p.ldo;
 
   auto load_vec = [&](const float* base, int col, float fill) {
     return base != nullptr ? __ldg(reinterpret_cast<const float4*>(base + col + tc)) : make_float4(fill, fill, fill, fill);
@@ -143,8 +181,8 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = row0 + 4 * i + tr;
-      res[i] = (r < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)r * p.ldr + col + tc)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      res[i] = (FULL || r < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)r * p.ldr + col + tc)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
 
@@ -153,7 +191,7 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
   float ln_nmu = 0.f, ln_rstd = 0.f;
   if constexpr (T::kLn) {
     const int r = row0 + lane;
-    if (r < p.M) {
+    if (FULL || r < p.M) {
       const float4* st = reinterpret_cast<const float4*>(p.ln_stats + (long long)r * p.ln_slices * 2);
       float sum = 0.f, sq = 0.f;
       for (int j = 0; j < p.ln_slices / 2; ++j) {  // fixed order: deterministic
@@ -204,22 +242,25 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
           const float2 hi = __ffma2_rn(make_float2(a.z, a.w), one2, make_float2(b4.z, b4.w));
           a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
         }
-        {
-          constexpr int kDeg = T::kHiLo ? 6 : 4;
-          const float2 lo = gelu_erf2<kDeg>(make_float2(a.x, a.y)), hi = gelu_erf2<kDeg>(make_float2(a.z, a.w));
+        if constexpr (T::kHiLo) {
+          const float2 lo = gelu_erf2<6>(make_float2(a.x, a.y)), hi = gelu_erf2<6>(make_float2(a.z, a.w));
+          a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
+        } else {
+          float2 lo = make_float2(a.x, a.y), hi = make_float2(a.z, a.w);
+          gelu_erf2x2<4>(lo, hi);
           a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
         }
-        if (r >= p.M) continue;
+        if (!FULL && r >= p.M) continue;
         uint2 w;
-        w.x = pack16(a.x, a.y, p.bf16);
-        w.y = pack16(a.z, a.w, p.bf16);
-        uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + (long long)r * p.ldo + col + tc;
+        w.x = pack16(a.x, a.y, kBf);
+        w.y = pack16(a.z, a.w, kBf);
+        uint16_t* orow = out16_base + (long long)i * out16_step + col;
         *reinterpret_cast<uint2*>(orow) = w;
         if constexpr (T::kHiLo) {  // lo = 16-bit(v - hi): hi + lo carries ~22 mantissa bits to the next split GEMM
-          const float2 h0 = unpack16(w.x, p.bf16), h1 = unpack16(w.y, p.bf16);
+          const float2 h0 = unpack16(w.x, kBf), h1 = unpack16(w.y, kBf);
           uint2 l;
-          l.x = pack16(a.x - h0.x, a.y - h0.y, p.bf16);
-          l.y = pack16(a.z - h1.x, a.w - h1.y, p.bf16);
+          l.x = pack16(a.x - h0.x, a.y - h0.y, kBf);
+          l.y = pack16(a.z - h1.x, a.w - h1.y, kBf);
           *reinterpret_cast<uint2*>(orow + p.lo_off) = l;
         }
       }
@@ -263,11 +304,11 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
       const int r = row0 + 4 * i + tr;
       if constexpr (T::kHalfOut) {
         uint2 w;
-        w.x = pack16(a[i].x, a[i].y, p.bf16);
-        w.y = pack16(a[i].z, a[i].w, p.bf16);
-        if (r < p.M) *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out) + (long long)r * p.ldo + col + tc) = w;
+        w.x = pack16(a[i].x, a[i].y, kBf);
+        w.y = pack16(a[i].z, a[i].w, kBf);
+        if (FULL || r < p.M) *reinterpret_cast<uint2*>(out16_base + (long long)i * out16_step + col) = w;
       } else if constexpr (EPI == EPI_PATCH_F32) {
-        if (r < p.M) {
+        if (FULL || r < p.M) {
           const int img = r / p.patches, pi = r % p.patches;
           const float4 p4 = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)(1 + pi) * p.N + col + tc));
           float4 o = a[i];
@@ -276,12 +317,12 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col + tc) = o;
         }
       } else {
-        if (r < p.M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + col + tc) = a[i];
+        if (FULL || r < p.M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)r * p.ldo + col + tc) = a[i];
         if constexpr (T::kStats) {
           uint2 w;
-          w.x = pack16(a[i].x, a[i].y, p.bf16);
-          w.y = pack16(a[i].z, a[i].w, p.bf16);
-          if (r < p.M) *reinterpret_cast<uint2*>(p.out16 + (long long)r * p.ldo16 + col + tc) = w;
+          w.x = pack16(a[i].x, a[i].y, kBf);
+          w.y = pack16(a[i].z, a[i].w, kBf);
+          if (FULL || r < p.M) *reinterpret_cast<uint2*>(p.out16 + (long long)r * p.ldo16 + col + tc) = w;
         }
       }
     }
@@ -312,7 +353,7 @@ __device__ __forceinline__ void epilogue_warp(const KParams& p, uint32_t tmem_ac
       const float tot_s = ks + __shfl_xor_sync(0xffffffffu, ss, 1);
       const float tot_q = kq + __shfl_xor_sync(0xffffffffu, sq, 1);
       const int r = row0 + 4 * (lane & 7) + tr;
-      if (r < p.M)
+      if (FULL || r < p.M)
         *reinterpret_cast<float2*>(p.stats_out + ((long long)r * (p.N / kLnSliceCols) + col64 / kLnSliceCols) * 2) =
             make_float2(tot_s, tot_q);
     }
@@ -407,9 +448,10 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kEpiSmemBytes + BAR_BYTES + 1024;  // +1024: alignment
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool BF16, bool FULL>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const KParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ KParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -512,8 +554,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
-      epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * BLOCK_M + q * 32, n_blk * BN, half * (BN / 2),
-                         (half + 1) * (BN / 2), stage, &tfull_bar[as], aph, 4);
+      epilogue_warp<EPI, BF16, FULL>(p, tmem_base + as * BN, q, lane, m_blk * BLOCK_M + q * 32, n_blk * BN, half * (BN / 2),
+                                     (half + 1) * (BN / 2), stage, &tfull_bar[as], aph, 4);
       // all TMEM reads of this accumulator are complete (wait::ld): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -537,20 +579,20 @@ struct Cfg2 {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;    // this CTA's 128 rows of A: 16 KB
   static constexpr int B_BYTES = (BN / 2) * BLOCK_K * 2;   // this CTA's 128 rows of W: 16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB per CTA per stage
-  static constexpr int STAGES = 6;
+  static constexpr int STAGES = 6;  // (4 and 5 stages measure the same on every layer shape: tools/bench_gemm_shapes.py)
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = 256;
   static constexpr int EPI_BYTES = kNumEpiWarps * kStageTileBytes;
-  static constexpr int THREADS = kThreads;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
 };
 
 // Variants that were measured and dropped (clusters of 4 with the W tile multicast between two pairs; mixed 4+2 clusters
 // with a dynamic scheduler; 16 epilogue warps) are described with their numbers in DESIGN.md section 8; their code is in
 // the history (commit 87a3dc2), not in the product library.
-template <int EPI>
-__global__ void __launch_bounds__(Cfg2::THREADS, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const KParams p) {
+template <int EPI, bool BF16, bool FULL>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const __grid_constant__ KParams p) {
   using C = Cfg2;
   constexpr int BN = C::BN;
   extern __shared__ uint8_t smem_raw[];
@@ -660,8 +702,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
-      epilogue_warp<EPI>(p, tmem_base + as * BN, q, lane, m_blk * 2 * BLOCK_M + rank * BLOCK_M + q * 32, n_blk * BN,
-                         part * PCOLS, (part + 1) * PCOLS, stage, &tfull_bar[as], aph, 14);
+      epilogue_warp<EPI, BF16, FULL>(p, tmem_base + as * BN, q, lane, m_blk * 2 * BLOCK_M + rank * BLOCK_M + q * 32,
+                                     n_blk * BN, part * PCOLS, (part + 1) * PCOLS, stage, &tfull_bar[as], aph, 14);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty_bar[as]), 0));
@@ -699,34 +741,34 @@ KParams make_params(const GemmArgs& a, int umma_m, int umma_n) {
   return p;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool BF16, bool FULL>
 int launch_one(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   using C = Cfg<BN>;
-  KB_TRY_ATTR((gemm_kernel<BN, EPI>), C::SMEM_BYTES);
+  KB_TRY_ATTR((gemm_kernel<BN, EPI, BF16, FULL>), C::SMEM_BYTES);
   const KParams p = make_params(a, BLOCK_M, BN);
   const int tiles = ((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BN - 1) / BN);
   int grid = num_sms();
   if (tiles < grid) grid = tiles;
   profile_gemm_tag(a.M, a.N, a.K, a.epi);
   profile_gemm_begin(stream);
-  gemm_kernel<BN, EPI><<<grid, kThreads, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_kernel<BN, EPI, BF16, FULL><<<grid, kThreads, C::SMEM_BYTES, stream>>>(ta, tb, p);
   profile_gemm_end(stream, 2.0 * a.M * a.N * a.K);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }
 
-template <int EPI>
+template <int EPI, bool BF16, bool FULL>
 int launch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   using C = Cfg2;
-  KB_TRY_ATTR((gemm2_kernel<EPI>), C::SMEM_BYTES);
-  const KParams p = make_params(a, 2 * BLOCK_M, C::BN);
-  const int tiles = ((a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((a.N + C::BN - 1) / C::BN);
+  KB_TRY_ATTR((gemm2_kernel<EPI, BF16, FULL>), C::SMEM_BYTES);
+  const KParams p = make_params(a, 2 * BLOCK_M, 256);
+  const int tiles = ((a.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * ((a.N + 256 - 1) / 256);
   int clusters = num_sms() / 2;  // one CTA per SM (227 KB of shared memory each); 148 SMs = 74 pairs, all co-resident
   if (tiles < clusters) clusters = tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * clusters));
-  cfg.blockDim = dim3(C::THREADS);
+  cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute at;
@@ -735,32 +777,47 @@ int launch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb,
   cfg.attrs = &at; cfg.numAttrs = 1;
   profile_gemm_tag(a.M, a.N, a.K, a.epi);
   profile_gemm_begin(stream);
-  KB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm2_kernel<EPI>, ta, tb, p));
+  KB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm2_kernel<EPI, BF16, FULL>, ta, tb, p));
   profile_gemm_end(stream, 2.0 * a.M * a.N * a.K);
   note_launch();
   KB_CUDA_CHECK(cudaGetLastError());
   return KB_OK;
 }
 
-#define KB_DISPATCH_EPI(FN, ...)                                                             \
-  switch (a.epi) {                                                                           \
-    case EPI_BIAS_HALF: return FN<__VA_ARGS__ EPI_BIAS_HALF>(a, ta, tb, stream);             \
-    case EPI_BIAS_GELU_HALF: return FN<__VA_ARGS__ EPI_BIAS_GELU_HALF>(a, ta, tb, stream);   \
-    case EPI_RESID_F32: return FN<__VA_ARGS__ EPI_RESID_F32>(a, ta, tb, stream);             \
-    case EPI_BIAS_F32: return FN<__VA_ARGS__ EPI_BIAS_F32>(a, ta, tb, stream);               \
-    case EPI_PATCH_F32: return FN<__VA_ARGS__ EPI_PATCH_F32>(a, ta, tb, stream);             \
-    case EPI_RESID_F32_STATS: return FN<__VA_ARGS__ EPI_RESID_F32_STATS>(a, ta, tb, stream); \
-    case EPI_LN_BIAS_HALF: return FN<__VA_ARGS__ EPI_LN_BIAS_HALF>(a, ta, tb, stream);       \
-    case EPI_LN_BIAS_GELU_HALF: return FN<__VA_ARGS__ EPI_LN_BIAS_GELU_HALF>(a, ta, tb, stream); \
-    case EPI_BIAS_GELU_HILO: return FN<__VA_ARGS__ EPI_BIAS_GELU_HILO>(a, ta, tb, stream);   \
-    default: return set_error(KB_ERR_ARG, "gemm: unknown epilogue %d", a.epi);               \
+// One kernel per (epilogue, 16-bit format, full / ragged rows): the same problem always runs the same kernel. FULL = every
+// row tile of the problem is complete (M a multiple of the tile height), so the epilogue carries no per-row guards.
+#define KB_DISPATCH_EPI(FN, ...)                                                                       \
+  switch (a.epi) {                                                                                     \
+    case EPI_BIAS_HALF: return FN<__VA_ARGS__ EPI_BIAS_HALF, BF16, FULL>(a, ta, tb, stream);           \
+    case EPI_BIAS_GELU_HALF: return FN<__VA_ARGS__ EPI_BIAS_GELU_HALF, BF16, FULL>(a, ta, tb, stream); \
+    case EPI_RESID_F32: return FN<__VA_ARGS__ EPI_RESID_F32, BF16, FULL>(a, ta, tb, stream);           \
+    case EPI_BIAS_F32: return FN<__VA_ARGS__ EPI_BIAS_F32, BF16, FULL>(a, ta, tb, stream);             \
+    case EPI_PATCH_F32: return FN<__VA_ARGS__ EPI_PATCH_F32, BF16, FULL>(a, ta, tb, stream);           \
+    case EPI_RESID_F32_STATS: return FN<__VA_ARGS__ EPI_RESID_F32_STATS, BF16, FULL>(a, ta, tb, stream); \
+    case EPI_LN_BIAS_HALF: return FN<__VA_ARGS__ EPI_LN_BIAS_HALF, BF16, FULL>(a, ta, tb, stream);     \
+    case EPI_LN_BIAS_GELU_HALF: return FN<__VA_ARGS__ EPI_LN_BIAS_GELU_HALF, BF16, FULL>(a, ta, tb, stream); \
+    case EPI_BIAS_GELU_HILO: return FN<__VA_ARGS__ EPI_BIAS_GELU_HILO, BF16, FULL>(a, ta, tb, stream); \
+    default: return set_error(KB_ERR_ARG, "gemm: unknown epilogue %d", a.epi);                         \
   }
 
+template <bool BF16, bool FULL>
 int dispatch_128(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   KB_DISPATCH_EPI(launch_one, 128, )
 }
+template <bool BF16, bool FULL>
 int dispatch_pair(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
   KB_DISPATCH_EPI(launch_pair, )
+}
+template <bool PAIR>
+int dispatch_variant(const GemmArgs& a, const CUtensorMap& ta, const CUtensorMap& tb, cudaStream_t stream) {
+  const bool full = a.M % (PAIR ? 2 * BLOCK_M : BLOCK_M) == 0;
+  if constexpr (PAIR) {
+    if (a.bf16) return full ? dispatch_pair<true, true>(a, ta, tb, stream) : dispatch_pair<true, false>(a, ta, tb, stream);
+    return full ? dispatch_pair<false, true>(a, ta, tb, stream) : dispatch_pair<false, false>(a, ta, tb, stream);
+  } else {
+    if (a.bf16) return full ? dispatch_128<true, true>(a, ta, tb, stream) : dispatch_128<true, false>(a, ta, tb, stream);
+    return full ? dispatch_128<false, true>(a, ta, tb, stream) : dispatch_128<false, false>(a, ta, tb, stream);
+  }
 }
 
 }  // namespace
@@ -795,7 +852,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   rc = get_tmap_2d(a.W, dt, a.N, w_cols, a.ldw, 128, &tb);
   if (rc) return rc;
-  return pair ? dispatch_pair(a, ta, tb, stream) : dispatch_128(a, ta, tb, stream);
+  return pair ? dispatch_variant<true>(a, ta, tb, stream) : dispatch_variant<false>(a, ta, tb, stream);
 }
 
 }  // namespace kb

@@ -123,6 +123,11 @@ constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
+// Register re-partitioning between warp roles (whole warpgroups of 4 consecutive warps must execute the same one):
+// the single-thread roles give registers back, the epilogue / softmax warpgroups take them.
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: TMEM alloc, fences, MMA, commit, ld
 // ----------------------------------------------------------------------------------------------

@@ -335,11 +335,40 @@ def make_transform_goldens():
     print("transform:", {k: v.shape for k, v in out.items()})
 
 
+def make_seg_eval_goldens():
+    """The reference's slide-level segmentation metrics (segment_utils.py:91-152) on a synthetic mask pyramid served by
+    oracle/fake_openslide.py (openslide itself and the mask TIFFs are not available offline)."""
+    from oracle import fake_openslide
+
+    mask, probs = fake_openslide.synthetic_case()
+    with fake_openslide.installed(mask):
+        for m in ("segment_utils",):
+            sys.modules.pop(m, None)  # re-import against the fake module
+        if "h5py" not in sys.modules:
+            try:
+                __import__("h5py")
+            except ImportError:
+                sys.modules["h5py"] = types.ModuleType("h5py")
+        sys.path.insert(0, os.path.join(REF, "WSI_evaluation"))
+        import segment_utils as seg
+
+        auc, thr = seg.eval_seg_auc(probs, "mask.tif", patch_size=224)
+        dice = {t: seg.eval_seg_coarse(probs, "mask.tif", patch_size=224, thd=t) for t in (0.3, 0.5, float(thr))}
+        empty = seg.eval_seg_coarse({k: 0.0 for k in probs}, "mask.tif", patch_size=224, thd=0.5)
+    np.savez_compressed(os.path.join(OUT, "seg_eval.npz"), auc=np.float64(auc), thr=np.float64(thr),
+                        dice_thd=np.array(list(dice.keys()), dtype=np.float64), dice=np.array(list(dice.values()), dtype=np.float64),
+                        dice_no_prediction=np.float64(empty), n_tiles=np.int64(len(probs)))
+    print("seg_eval: auc", auc, "thr", thr, "dice", dice, "no prediction", empty)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     if len(sys.argv) > 1 and sys.argv[1] == "transform":
         make_transform_goldens()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "seg_eval":
+        make_seg_eval_goldens()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "model":
         make_model_goldens()
@@ -347,5 +376,6 @@ if __name__ == "__main__":
     make_wsi_goldens()
     make_model_goldens()
     make_transform_goldens()
+    make_seg_eval_goldens()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

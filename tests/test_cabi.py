@@ -65,7 +65,9 @@ def test_no_environment_switch_changes_the_numerics():
         assert not [n for n in names if "gemm2d" in n], "dynamic-scheduler GEMM variant still compiled"
         pair = [n for n in names if re.search(r"\d+gemm2_kernelI", n)]
         single = [n for n in names if re.search(r"\d+gemm_kernelI", n)]
-        assert len(pair) == 9 and len(single) == 9, (pair, single)  # one instantiation per epilogue and main-loop variant
+        # one instantiation per (epilogue, 16-bit format, full / ragged row tiles) and main-loop variant: which one runs is a
+        # function of the problem (shape and dtype) only
+        assert len(pair) == 9 * 4 and len(single) == 9 * 4, (len(pair), len(single))
 
 
 def test_config_struct_layout_matches_header():

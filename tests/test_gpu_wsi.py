@@ -172,3 +172,22 @@ def test_slide_level_flow_matches_the_reference_flow(task):
     # ... and without screening the ensemble is the scripts' seeded random draw
     got2 = zero_shot_slide(task, {"model": prod, "tokenizer": tok}, prompts, feats.to(DEV), coords, DEV, topn=7, prompt_screening=False)
     assert type(got2) is type(got)
+
+
+def test_zero_shot_segment_returns_the_reference_metrics(data):
+    """`zero_shot_segment` end to end (segment_utils.py:44-60): device similarity + refine, then the AUROC / Dice of the
+    reference's metric code on a mask served by the fake openslide (oracle/fake_openslide.py): same numbers as the metric
+    functions applied to the oracle's refined probabilities (thresholds sit far from any tile's probability)."""
+    from keep_b200 import seg_eval, wsi
+    from oracle import fake_openslide
+
+    feats, coords, cls2, _, _ = data
+    mask = np.zeros((40 * 112 + 112, 40 * 112 + 112), dtype=np.uint8)
+    mask[: 20 * 112, : 26 * 112] = 255
+    probs = wo.tile_probs(cls2.cpu(), feats.cpu())[1]
+    exp_probs = wo.refine_seg_segment(probs.numpy(), coords, patch_size=112, overlap=True)
+    with fake_openslide.installed(mask):
+        auc, dice = wsi.zero_shot_segment(cls2, feats, coords, "mask.tif", patch_size=112, overlap=True)
+        exp_auc, thd = seg_eval.eval_seg_auc(exp_probs, "mask.tif", patch_size=112)
+        exp_dice = seg_eval.eval_seg_coarse(exp_probs, "mask.tif", patch_size=112, thd=thd)
+    assert abs(auc - exp_auc) < 2e-3 and abs(dice - exp_dice) < 2e-2, (auc, exp_auc, dice, exp_dice)

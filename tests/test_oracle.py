@@ -145,3 +145,26 @@ def test_transform_oracle_matches_live_pil_when_available():
     for (H, W) in [(257, 311), (640, 480), (225, 224), (150, 333)]:
         img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
         assert np.array_equal(to.resize_center_crop(img), np.asarray(tf(PIL.fromarray(img)))), (H, W)
+
+
+def test_seg_eval_matches_the_reference_metrics(golden_dir):
+    """keep_b200.seg_eval (AUROC + Youden threshold, coarse Dice at the level nearest 16x) against the reference's own
+    eval_seg_auc / eval_seg_coarse (WSI_evaluation/segment_utils.py:91-152) run on the same synthetic mask pyramid
+    (tests/golden/seg_eval.npz, made by `python -m oracle.make_golden seg_eval` with oracle/fake_openslide.py standing in
+    for openslide, which is not available offline)."""
+    from keep_b200 import seg_eval
+    from oracle import fake_openslide
+
+    g = common.load_golden(golden_dir, "seg_eval.npz")
+    mask, probs = fake_openslide.synthetic_case()
+    assert len(probs) == int(g["n_tiles"])
+    with fake_openslide.installed(mask):
+        auc, thr = seg_eval.eval_seg_auc(probs, "mask.tif", patch_size=224)
+        assert auc == pytest.approx(float(g["auc"]), abs=1e-12) and thr == pytest.approx(float(g["thr"]), abs=1e-12)
+        for t, d in zip(g["dice_thd"], g["dice"]):
+            assert seg_eval.eval_seg_coarse(probs, "mask.tif", patch_size=224, thd=float(t)) == pytest.approx(float(d), abs=1e-12)
+        # nothing predicted: Dice 0 (the reference's "1 when both are empty" branch needs an empty mask as well)
+        assert seg_eval.eval_seg_coarse({k: 0.0 for k in probs}, "mask.tif", thd=0.5) == float(g["dice_no_prediction"])
+        assert seg_eval.eval_seg_coarse({}, "mask.tif") == 0.0
+    with fake_openslide.installed(np.zeros_like(mask)):
+        assert seg_eval.eval_seg_coarse({k: 0.0 for k in probs}, "mask.tif", thd=0.5) == 1
