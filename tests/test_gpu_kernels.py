@@ -526,3 +526,59 @@ def test_empty_and_single_element_inputs():
     s = ops.prompt_scores(x, cls, 1, 2)                          # one tile, one two-class classifier
     l2 = (F.normalize(x, dim=-1) @ cls).flatten().sort(descending=True).values
     assert abs(s.item() - ((l2[0] - l2[1]) - (l2[0] + l2[1] - 1).abs()).item()) < 3e-4  # TF32 logits: ~3e-5 each
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_gemm_full_and_ragged_row_tiles_are_the_same_arithmetic(dtype):
+    """The GEMMs run one kernel per (epilogue, 16-bit format, full / ragged row tiles): rows shared by a problem whose M is
+    a multiple of the tile height (unguarded epilogue) and by the same problem with a ragged last tile (guarded epilogue)
+    must come out bit for bit the same, on both main-loop variants (CTA pairs: 256-row tiles; single CTA: 128-row tiles)."""
+    from keep_b200 import ops
+
+    for (M_full, extra, N, K) in ((256 * 80, 37, 1024, 256), (128 * 3, 5, 256, 128)):
+        g = torch.Generator(device="cpu").manual_seed(M_full + N)
+        a = (torch.randn(M_full + extra, K, generator=g) * 0.5).to(dtype).to(DEV)
+        w = (torch.randn(N, K, generator=g) * 0.05).to(dtype).to(DEV)
+        bias = torch.randn(N, generator=g).to(DEV)
+        gamma = torch.rand(N, generator=g).to(DEV)
+        x0 = torch.randn(M_full + extra, N, generator=g).to(DEV)
+        for epi in (ops.EPI_BIAS_HALF, ops.EPI_BIAS_GELU_HALF, ops.EPI_BIAS_F32):
+            full = ops.gemm(a[:M_full], w, epi, bias=bias)
+            rag = ops.gemm(a, w, epi, bias=bias)
+            assert torch.equal(full, rag[:M_full]), (epi, M_full, dtype)
+            ref = a.float() @ w.float().T + bias
+            if epi == ops.EPI_BIAS_GELU_HALF:
+                ref = F.gelu(ref)
+            assert _rel(rag.float(), ref) < (2e-2 if dtype == torch.bfloat16 else 3e-3)
+        xf, xr = x0[:M_full].clone(), x0.clone()
+        ops.gemm(a[:M_full], w, ops.EPI_RESID_F32, bias=bias, gamma=gamma, resid=xf, out=xf)
+        ops.gemm(a, w, ops.EPI_RESID_F32, bias=bias, gamma=gamma, resid=xr, out=xr)
+        assert torch.equal(xf, xr[:M_full])
+        if N % 64 == 0:
+            xf, xr = x0[:M_full].clone(), x0.clone()
+            f16, fst = ops.gemm_resid_stats(a[:M_full], w, xf, bias=bias, gamma=gamma)
+            r16, rst = ops.gemm_resid_stats(a, w, xr, bias=bias, gamma=gamma)
+            assert torch.equal(xf, xr[:M_full]) and torch.equal(f16, r16[:M_full]) and torch.equal(fst, rst[:M_full])
+
+
+@pytest.mark.parametrize("N,P,group", [(1, 32, 2), (7, 16, 0), (129, 32, 2), (5000, 32, 2), (10_000, 32, 2), (9_999, 64, 4),
+                                       (19_003, 256, 4), (19_003, 128, 2), (40_000, 256, 16), (20_000, 144, 0), (30_001, 512, 2)])
+def test_similarity_tile_shapes(N, P, group):
+    """Every scheduling variant of the TF32 similarity kernel: rows spread over all SMs in tiles of fewer than 128 rows
+    (small N), 128-row single-CTA tiles, CTA pairs on 256-row tiles with half a classifier block each (wide P, many rows),
+    ragged last tiles, several column tiles (P > 256) - logits and grouped probabilities against fp32, with and without the
+    logits output."""
+    from keep_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(N * 7 + P)
+    feats = (torch.randn(N, 768, generator=g) * 1.5).to(DEV)
+    cls = F.normalize(torch.randn(768, P, generator=g), dim=0).to(DEV)
+    ref = F.normalize(feats, dim=-1) @ cls
+    gg = group or P
+    ref_p = torch.softmax(ref.view(N, P // gg, gg) * 10, -1).view(N, P)
+    lg, pr = ops.similarity(feats, cls, group=group, temp=10.0)
+    assert (lg - ref).abs().max().item() < 2e-4 and (pr - ref_p).abs().max().item() < 1e-3
+    assert (pr.view(N, P // gg, gg).sum(-1) - 1).abs().max().item() < 1e-5
+    if 16 % gg == 0:
+        none, pr2 = ops.similarity(feats, cls, group=group, temp=10.0, want_logits=False)
+        assert none is None and torch.equal(pr2, pr)
