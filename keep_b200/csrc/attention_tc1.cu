@@ -34,12 +34,10 @@ namespace kb {
 namespace {
 
 constexpr int kAtcThreads = 512;
-constexpr int kMaxSpad = 224;                 // 2 * S_pad + 64 (O) <= 512 TMEM columns
+constexpr int kMaxSpadShared = 224;           // separate O accumulator: 2 * S_pad + 64 (O) <= 512 TMEM columns
+constexpr int kMaxSpad = 256;                 // O inside the unit's own region (below): 2 * S_pad <= 512
 constexpr int Q_TILE_BYTES = 128 * 128;       // 128 rows x 64 x 16-bit
-constexpr int K_TILE_BYTES = kMaxSpad * 128;  // 28 KB
-constexpr int QK_SLOT_BYTES = 2 * Q_TILE_BYTES + K_TILE_BYTES;  // 60 KB (multiple of 1024)
-constexpr int V_SLOT_BYTES = kMaxSpad * 128;  // 28 KB
-constexpr int kQkSlots = 2, kVSlots = 3;
+constexpr int kQkSlots = 2;
 
 struct Atc1Params {
   int B, S, H, S_pad, n_qt;
@@ -55,14 +53,23 @@ struct Atc1Params {
   long long* trace;   // optional [64 units][16 events] clock64 stamps of CTA 0 (debug/profiling aid), or null
 };
 
-struct Smem {  // offsets inside the 1024-aligned dynamic smem block
-  static constexpr int qk = 0;
-  static constexpr int v = kQkSlots * QK_SLOT_BYTES;
-  static constexpr int bias = v + kVSlots * V_SLOT_BYTES;   // [kVSlots][256] float: 0 / -inf per key
-  static constexpr int meta = bias + kVSlots * 256 * 4;     // [kVSlots] int: index of the first masked key
-  static constexpr int rowsum = meta + 64;                  // [2 regions][2 parities][128] float
-  static constexpr int bars = rowsum + 2 * 2 * 128 * 4;
-  static constexpr int total = bars + 256;
+// Shared-memory layout (offsets inside the 1024-aligned dynamic block), sized by S_pad: Q/K slots of 2 x 16 KB + S_pad
+// key rows, V slots of S_pad rows (3 of them up to 224 keys, 2 beyond: 256 keys take 64 + 32 KB per slot)
+struct Smem {
+  int qk_slot, v_slot, v_slots;
+  int qk, v, bias, meta, rowsum, bars, total;
+  __host__ __device__ explicit Smem(int S_pad) {
+    qk_slot = 2 * Q_TILE_BYTES + S_pad * 128;   // multiple of 1024 (S_pad is a multiple of 16)
+    v_slot = S_pad * 128;
+    v_slots = S_pad > kMaxSpadShared ? 2 : 3;
+    qk = 0;
+    v = kQkSlots * qk_slot;
+    bias = v + v_slots * v_slot;              // [v_slots][256] float: 0 / -inf per key
+    meta = bias + v_slots * 256 * 4;          // [v_slots] int: index of the first masked key
+    rowsum = meta + 64;                       // [2 regions][2 parities][128] float
+    bars = rowsum + 2 * 2 * 128 * 4;
+    total = bars + 256;
+  }
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -99,10 +106,11 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   constexpr int kBf = BF16 ? 1 : 0;  // compile-time 16-bit format: one F2FP per pair in the softmax, no predicated twin
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* s_bias = reinterpret_cast<float*>(smem + Smem::bias);
-  int* s_meta = reinterpret_cast<int*>(smem + Smem::meta);
-  float* s_rowsum = reinterpret_cast<float*>(smem + Smem::rowsum);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+  const Smem L(p.S_pad);
+  float* s_bias = reinterpret_cast<float*>(smem + L.bias);
+  int* s_meta = reinterpret_cast<int*>(smem + L.meta);
+  float* s_rowsum = reinterpret_cast<float*>(smem + L.rowsum);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* qk_full = bars;        // [2] TMA -> MMA
   uint64_t* qk_empty = bars + 2;   // [2] MMA (last S of the head committed) -> TMA
   uint64_t* v_full = bars + 4;     // [3] TMA + key-bias writer -> MMA, softmax
@@ -116,7 +124,13 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_my = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // heads of this CTA
   const int U = n_my * p.n_qt;                                                          // units of this CTA
-  const uint32_t o_col = 2 * p.S_pad;
+  // O accumulator (64 columns): up to 224 keys one shared accumulator after the two S regions; beyond (<= 256 keys: the
+  // padded prompt bank) the regions fill TMEM and O(u) lives in the upper half of ITS OWN region, which is free once the
+  // softmax has replaced the fp32 scores by the packed 16-bit P in the lower half. S(u+2) then also waits for O(u) to
+  // be drained (o_free) before it overwrites the region.
+  const bool o_in_region = p.S_pad > kMaxSpadShared;
+  const uint32_t o_col0 = o_in_region ? (uint32_t)(p.S_pad / 2) : 2u * p.S_pad;
+  const uint32_t o_col1 = o_in_region ? (uint32_t)(p.S_pad + p.S_pad / 2) : 2u * p.S_pad;
 
   if (warp == 13 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -151,20 +165,22 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     // ===================== producer: TMA tiles + key bias =====================
     int b = (int)blockIdx.x / p.H, h = (int)blockIdx.x - b * p.H;
     const int db = (int)gridDim.x / p.H, dh = (int)gridDim.x - db * p.H;
+    int vs = 0;
+    uint32_t vph = 0;  // V slot of head j and its use parity, advanced with the head (no divisions)
     for (int j = 0; j < n_my; ++j, b += db, h += dh) {
       if (h >= p.H) { h -= p.H; ++b; }
       const int row0 = b * p.S;
-      const int qs = j & 1, vs = j % 3;
+      const int qs = j & 1;
       if (lane == 0) {
         mbar_wait(&qk_empty[qs], ((j >> 1) & 1) ^ 1, 21);
-        uint8_t* base = smem + Smem::qk + qs * QK_SLOT_BYTES;
+        uint8_t* base = smem + L.qk + qs * L.qk_slot;
         mbar_arrive_expect_tx(&qk_full[qs], p.n_qt * Q_TILE_BYTES + kv_bytes);
         for (int t = 0; t < p.n_qt; ++t)
           tma_load_2d(&tmap_q, &qk_full[qs], base + t * Q_TILE_BYTES, h * 64, row0 + t * 128);
         tma_load_2d(&tmap_kv, &qk_full[qs], base + 2 * Q_TILE_BYTES, (p.H + h) * 64, row0);
-        mbar_wait(&v_empty[vs], ((j / 3) & 1) ^ 1, 22);
+        mbar_wait(&v_empty[vs], vph ^ 1, 22);
         mbar_arrive_expect_tx(&v_full[vs], kv_bytes);
-        tma_load_2d(&tmap_kv, &v_full[vs], smem + Smem::v + vs * V_SLOT_BYTES, (2 * p.H + h) * 64, row0);
+        tma_load_2d(&tmap_kv, &v_full[vs], smem + L.v + vs * L.v_slot, (2 * p.H + h) * 64, row0);
       }
       __syncwarp();
       // additive key bias: 0 for attended keys, -inf for masked keys and the padding up to S_pad
@@ -180,20 +196,24 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if (lane == 0) s_meta[vs] = first_bad;  // 32-key chunks entirely below it need no bias at all
       __syncwarp();
       if (lane == 0) mbar_arrive(&v_full[vs]);
+      if (++vs == L.v_slots) { vs = 0; vph ^= 1; }
     }
   } else if (warp == 12) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // (head j, query tile t) of the next S / PV unit, advanced with counters: no divisions on this thread
       int sj = 0, st = 0, pj = 0, pt = 0;
+      int pvs = 0;
+      uint32_t pvph = 0;  // V slot / parity of head pj
       auto issue_s = [&](int u) {
         const int j = sj, t = st, qs = j & 1, r = u & 1;
         if (++st == p.n_qt) { st = 0; ++sj; }
         if (t == 0) mbar_wait(&qk_full[qs], (j >> 1) & 1, 23);
+        if (o_in_region && u >= 2) mbar_wait(o_free, (u - 2) & 1, 26);  // O(u-2) sits in this region: drained first
         tc_fence_after();
         // region r is free: PV(u-2) was issued before this in program order (the tensor pipe executes in order) and
         // softmax(u-2) finished reading S before p_ready(u-2), which PV(u-2) waited for
-        const uint8_t* base = smem + Smem::qk + qs * QK_SLOT_BYTES;
+        const uint8_t* base = smem + L.qk + qs * L.qk_slot;
         const uint64_t dq = make_smem_desc_sw128(smem_u32(base + t * Q_TILE_BYTES));
         const uint64_t dk = make_smem_desc_sw128(smem_u32(base + 2 * Q_TILE_BYTES));
 #pragma unroll
@@ -204,20 +224,29 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (t == p.n_qt - 1) umma_commit(&qk_empty[qs]);  // Q/K of this head are dead once these MMAs complete
       };
       auto issue_pv = [&](int u) {
-        const int j = pj, t = pt, vs = j % 3, r = u & 1;
-        if (++pt == p.n_qt) { pt = 0; ++pj; }
+        const int t = pt, vs = pvs, r = u & 1;
+        const uint32_t vph = pvph;
         mbar_wait(&p_ready[r], (u >> 1) & 1, 24);
-        if (t == 0) mbar_wait(&v_full[vs], (j / 3) & 1, 25);
-        if (u > 0) mbar_wait(o_free, (u - 1) & 1, 26);  // the output group has drained O of the previous unit
+        if (t == 0) mbar_wait(&v_full[vs], vph, 25);
+        // the output group has drained O of the previous unit (shared accumulator). With O in the regions this wait is not
+        // needed for the data, but it keeps this thread at most one o_free phase ahead, so the parity wait in issue_s
+        // (phase u-2) cannot be satisfied by a stale phase u-4
+        if (u > 0) mbar_wait(o_free, (u - 1) & 1, 26);
         tc_fence_after();
         if (p.trace != nullptr && blockIdx.x == 0 && u < 64) p.trace[u * 16 + EV_PV_WAITED] = clock64();
-        const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + Smem::v + vs * V_SLOT_BYTES));
+        const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + L.v + vs * L.v_slot));
         const int ksteps = p.S_pad / 16;
+        const uint32_t o_col = r ? o_col1 : o_col0;
         for (int k = 0; k < ksteps; ++k)  // 16 keys per MMA: P advances 8 TMEM columns, V advances 16 rows = 2048 B
           umma_f16_ts(tmem_base + o_col, tmem_base + r * p.S_pad + 8 * k, dv + 128 * k, p.idesc_pv, k != 0 ? 1u : 0u);
         umma_commit(o_ready);
         if (p.trace != nullptr && blockIdx.x == 0 && u < 64) p.trace[u * 16 + EV_PV_ISSUED] = clock64();
         if (t == p.n_qt - 1) umma_commit(&v_empty[vs]);
+        if (++pt == p.n_qt) {
+          pt = 0;
+          ++pj;
+          if (++pvs == L.v_slots) { pvs = 0; pvph ^= 1; }
+        }
       };
       if (U > 0) issue_s(0);
       if (U > 1) issue_s(1);
@@ -233,13 +262,22 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t t_row = tmem_base + g * p.S_pad + (uint32_t(q * 32) << 16);
     const int row_in_tile = q * 32 + lane;
     int uj = 0, ut = g;  // (head, tile) of unit u, advanced by two units per iteration
-    while (ut >= p.n_qt) { ut -= p.n_qt; ++uj; }
+    int uvs = 0;
+    uint32_t uvph = 0;   // V slot / parity of head uj
+    while (ut >= p.n_qt) {
+      ut -= p.n_qt; ++uj;
+      if (++uvs == L.v_slots) { uvs = 0; uvph ^= 1; }
+    }
     for (int u = g; u < U; u += 2) {
-      const int j = uj, vs = j % 3, t_here = ut;
+      const int vs = uvs, t_here = ut;
+      const uint32_t vph = uvph;
       ut += 2;
-      while (ut >= p.n_qt) { ut -= p.n_qt; ++uj; }
+      while (ut >= p.n_qt) {
+        ut -= p.n_qt; ++uj;
+        if (++uvs == L.v_slots) { uvs = 0; uvph ^= 1; }
+      }
       const int n = u >> 1;
-      mbar_wait(&v_full[vs], (j / 3) & 1, 27);  // key bias / meta visible
+      mbar_wait(&v_full[vs], vph, 27);  // key bias / meta visible
       const float* bias = s_bias + vs * 256;
       // warps whose 32 query rows all lie beyond S (tail of the last tile) skip the TMEM traffic: their P rows
       // stay whatever they were, the corresponding O rows are never stored
@@ -382,7 +420,7 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   } else if (warp < 4) {
     // ===================== output group: O / row sum -> context rows =====================
     const int q = warp & 3;
-    const uint32_t t_o = tmem_base + o_col + (uint32_t(q * 32) << 16);
+    const uint32_t t_o0 = tmem_base + o_col0 + (uint32_t(q * 32) << 16), t_o1 = tmem_base + o_col1 + (uint32_t(q * 32) << 16);
     const int row_in_tile = q * 32 + lane;
     int b = (int)blockIdx.x / p.H, h = (int)blockIdx.x - b * p.H, t = -1;
     const int db = (int)gridDim.x / p.H, dh = (int)gridDim.x - db * p.H;
@@ -401,6 +439,7 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       ATC_TRACE(u, EV_OUT_START);
       uint32_t va[32], vb[32];
       if (t * 128 + q * 32 < p.S) {  // warp-uniform: skip the tail warps of the last tile
+        const uint32_t t_o = r ? t_o1 : t_o0;
         tmem_ld_32x32(t_o, va);
         tmem_ld_32x32(t_o + 32, vb);
         tmem_ld_wait_dep(va);
@@ -466,7 +505,7 @@ int launch_attention_tc1(const void* qkv, void* out, int B, int S, int H, int bf
   if (rc) return rc;
   rc = get_tmap_2d(qkv, dt, rows, cols, cols, S_pad, &tkv);
   if (rc) return rc;
-  const int smem = Smem::total + 1024;
+  const int smem = Smem(S_pad).total + 1024;
   KB_TRY_ATTR(attention_tc1_kernel<true>, smem);
   KB_TRY_ATTR(attention_tc1_kernel<false>, smem);
   Atc1Params p;

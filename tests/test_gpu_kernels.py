@@ -152,11 +152,14 @@ def test_l2norm_and_tanh():
                                             (1, 1, 2, False), (2, 300, 2, True), (150, 1, 2, True), (23, 5, 3, True),
                                             (9, 12, 12, True), (40, 33, 2, False), (3, 56, 4, True), (3, 57, 4, True),
                                             (5, 64, 2, False), (2, 112, 3, True), (2, 113, 3, True), (3, 224, 2, False),
-                                            (2, 225, 2, True), (1, 512, 2, True), (2, 485, 2, False), (300, 197, 1, False)])
+                                            (2, 225, 2, True), (1, 512, 2, True), (2, 485, 2, False), (300, 197, 1, False),
+                                            (4, 240, 3, False), (3, 241, 2, True), (200, 256, 12, False), (2, 257, 2, True)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_attention(B, S, H, masked, dtype):
-    """Every shape class of the tcgen05 kernel: packed sequences (S <= 56, whole sequences of a head share one tile,
-    ragged last group), one to five KV blocks of up to 112 keys, ragged last query tile, key masks of random lengths."""
+    """Every shape class of the tcgen05 kernels: packed sequences (S <= 56, whole sequences of a head share one tile,
+    ragged last group), the single-tile kernel (65..224 keys with a shared O accumulator, 225..256 keys with O inside the
+    unit's own TMEM region; many units per CTA), two to five KV blocks of up to 112 keys beyond, ragged last query tile,
+    key masks of random lengths."""
     from keep_b200 import ops
 
     g = torch.Generator().manual_seed(S * 3 + H)

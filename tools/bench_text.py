@@ -46,6 +46,24 @@ def timed(inputs, chunk):
     return time.perf_counter() - t0, out
 
 
+def latency_b1(n_calls=200):
+    """The reference's own call pattern (WSI_evaluation/utils.py:67-74): one encode_text per class prompt, batch 1."""
+    one = {k: v[:1] for k, v in text.items()}
+    for _ in range(10):
+        model.encode_text(one)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(n_calls):
+        model.encode_text(one)
+    e1.record()
+    torch.cuda.synchronize()
+    return {"tokens": int(lens[0]), "calls": n_calls, "device_us_per_call": e0.elapsed_time(e1) * 1e3 / n_calls,
+            "wall_us_per_call": (time.perf_counter() - t0) * 1e6 / n_calls}
+
+
+b1 = latency_b1()
 t_trim, o_trim = timed(text, 4096)
 n_pad = min(P, 16384)
 t_pad, o_pad = timed({k: v[:n_pad] for k, v in padded.items()}, 1024)
@@ -58,5 +76,6 @@ line = {
     "padded_S256": {"prompts": n_pad, "prompts_per_s": n_pad / t_pad, "seconds": t_pad,
                     "frac_of_tensor_roofline": (n_pad / t_pad) * 45.904e9 / (peak * 1e12)},
     "max_abs_diff_trimmed_vs_padded": diff,
+    "batch_1_latency": b1,
 }
 print(json.dumps(line))

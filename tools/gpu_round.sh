@@ -25,7 +25,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:gem
   python bench.py --tiles 512 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > $OUT/${TAG}_ncu_full_bench.log 2>&1
 echo "ncu full exit $?"
 # the text tower (packed tcgen05 attention, split-operand GEMMs, embedding gather, fused pooler) and the WSI kernels
-timeout 600 ncu --set full --clock-control none -k 'regex:attention_tc_kernel|bert_embed|gemm_kernel|head_kernel|refine|prompt_score|score_reduce|sim_tc|resample|crop_kernel|table_' -c 40 -f -o $OUT/${TAG}_full_text_wsi \
+timeout 600 ncu --set full --clock-control none -k 'regex:attention_tc|bert_embed|gemm_kernel|head_kernel|refine|prompt_score|score_reduce|sim_tc|resample|crop_kernel|table_' -c 44 -f -o $OUT/${TAG}_full_text_wsi \
   python tools/profile_text_wsi.py > $OUT/${TAG}_ncu_text_wsi.log 2>&1
 echo "ncu text/wsi exit $?"
 # gpurun brings back at most 64 MiB: keep the raw pages (every metric of every captured launch) as CSV, drop the reports

@@ -1,6 +1,6 @@
 """One pass of the kernels that the tile benchmark does not exercise, for `ncu` (tools/gpu_round.sh): the text tower on a
 WSI-sized prompt set (high precision: packed tcgen05 attention, split-operand GEMMs, fused pooler) and on a padded S = 256
-batch (three key blocks), the similarity / screening / refine kernels at BASELINE sizes, and the uint8 resize."""
+batch (single-tile attention with O inside the unit's TMEM region), the similarity / screening / refine kernels at BASELINE sizes, and the uint8 resize."""
 import os
 import sys
 
@@ -30,6 +30,9 @@ side = 448
 coords = torch.stack(torch.meshgrid(torch.arange(side), torch.arange(side), indexing="ij"), -1).reshape(-1, 2)[:200_000].to(dev) * 112
 ops.refine(coords, p2, 224, True)
 preprocess(torch.randint(0, 256, (256, 256, 256, 3), device=dev, dtype=torch.uint8, generator=gd))
+qkv256 = torch.randn(512 * 256, 3 * 12 * 64, device=dev, generator=gd).half()   # one padded-BERT attention layer (512 prompts, S = 256)
+ops.attention(qkv256, 512, 256, 12)
+del qkv256
 g = torch.Generator().manual_seed(0)
 P = 512
 lens = torch.randint(4, 33, (P,), generator=g)

@@ -6,7 +6,9 @@
 
 Shapes are small (the tools slow kernels down 10-100x) but cover every role pipeline: the CTA-pair GEMM (two tiles per pair:
 both accumulator stages), the single-CTA GEMM in split-operand mode with the hi|lo GELU epilogue, both attention kernels
-(single tile; packed sequences; three key blocks), the TF32 similarity kernel, the fused fp32 head."""
+(single tile with the shared O accumulator and with O inside the unit's region; packed sequences; three key blocks), the
+TF32 similarity kernel (single CTA with direct stores and small row tiles; CTA pairs with staging tiles + TMA stores), the
+fused fp32 head."""
 import os
 import sys
 
@@ -30,7 +32,9 @@ ops.gemm_resid_stats(a, w, resid.clone(), bias=bias)
 x32, w32 = rn(300, 128), rn(256, 128) * 0.1
 h = ops.gemm_split(ops.cast_hilo(x32), ops.cast_hilo(w32), 128, ops.EPI_BIAS_GELU_HILO, ops.SPLIT_AW, bias=bias)
 assert (h[:, :256].float() + h[:, 256:].float() - F.gelu(x32 @ w32.T + bias)).abs().max() < 1e-3
-for B, S, H, masked in ((4, 197, 2, False), (40, 12, 2, True), (2, 300, 2, True), (3, 100, 2, True)):
+ab, wb = a[: 256 * 80 + 37].bfloat16(), w.bfloat16()                           # ragged row tiles, bf16 epilogue variants
+ops.gemm(ab, wb, ops.EPI_BIAS_GELU_HALF, bias=bias)
+for B, S, H, masked in ((4, 197, 2, False), (40, 12, 2, True), (2, 300, 2, True), (3, 100, 2, True), (3, 256, 2, True), (2, 240, 2, False)):
     qkv = rn(B * S, 3 * H * 64).half()
     mask = None
     if masked:
@@ -41,6 +45,9 @@ for B, S, H, masked in ((4, 197, 2, False), (40, 12, 2, True), (2, 300, 2, True)
 feats, cls = rn(2000, 768), F.normalize(rn(768, 32), dim=0)
 lg, pr = ops.similarity(feats, cls, group=2, temp=10.0)
 assert (lg - F.normalize(feats, dim=-1) @ cls).abs().max() < 1e-3
+big, cls128 = rn(19_200, 768), F.normalize(rn(768, 128), dim=0)                 # 75 pair tiles of 256 rows on 74 pairs
+lg, pr = ops.similarity(big, cls128, group=4, temp=10.0)
+assert (lg - F.normalize(big, dim=-1) @ cls128).abs().max() < 1e-3 and (pr.view(-1, 32, 4).sum(-1) - 1).abs().max() < 1e-4
 ops.prompt_scores(feats, F.normalize(rn(768, 64), dim=0), 16, 4, fused=True)
 ops.visual_head(rn(20, 1024), torch.ones(1024, device=dev), torch.zeros(1024, device=dev), 1e-6, rn(768, 1024) / 32, rn(768), rn(768, 768) / 27, rn(768))
 ops.pooler(rn(5, 768), rn(768, 768) / 27, rn(768))
