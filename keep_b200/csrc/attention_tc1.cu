@@ -184,16 +184,23 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       __syncwarp();
       // additive key bias: 0 for attended keys, -inf for masked keys and the padding up to S_pad
-      int first_bad = p.S_pad;
+      int first_bad = p.S_pad, last_ok = 0;
       for (int k = lane; k < p.S_pad; k += 32) {
         bool ok = k < p.S;
         if (ok && p.key_mask != nullptr) ok = p.key_mask[(long long)b * p.mask_stride + k] != 0;
         s_bias[vs * 256 + k] = ok ? 0.f : -INFINITY;
         if (!ok && k < first_bad) first_bad = k;
+        if (ok) last_ok = k;
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
-      if (lane == 0) s_meta[vs] = first_bad;  // 32-key chunks entirely below it need no bias at all
+      for (int o = 16; o > 0; o >>= 1) {
+        first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
+        last_ok = max(last_ok, __shfl_xor_sync(0xffffffffu, last_ok, o));
+      }
+      if (lane == 0) {
+        s_meta[vs] = first_bad;                       // 32-key chunks entirely below it need no bias at all
+        s_meta[4 + vs] = (last_ok + 16) / 16 * 16;    // keys from here on are all masked: exp(-inf) = 0 exactly, so neither
+      }                                               // the softmax nor the PV MMAs visit them (padded prompts: 16-32 of 256)
       __syncwarp();
       if (lane == 0) mbar_arrive(&v_full[vs]);
       if (++vs == L.v_slots) { vs = 0; vph ^= 1; }
@@ -235,7 +242,7 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         tc_fence_after();
         if (p.trace != nullptr && blockIdx.x == 0 && u < 64) p.trace[u * 16 + EV_PV_WAITED] = clock64();
         const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + L.v + vs * L.v_slot));
-        const int ksteps = p.S_pad / 16;
+        const int ksteps = s_meta[4 + vs] / 16;  // (v_full of this head was waited for at its first tile: the value is visible)
         const uint32_t o_col = r ? o_col1 : o_col0;
         for (int k = 0; k < ksteps; ++k)  // 16 keys per MMA: P advances 8 TMEM columns, V advances 16 rows = 2048 B
           umma_f16_ts(tmem_base + o_col, tmem_base + r * p.S_pad + 8 * k, dv + 128 * k, p.idesc_pv, k != 0 ? 1u : 0u);
@@ -283,7 +290,7 @@ attention_tc1_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       // stay whatever they were, the corresponding O rows are never stored
       const bool live = t_here * 128 + q * 32 < p.S;
       const int fast_end = live ? (s_meta[vs] & ~31) : 0;    // keys [0, fast_end) are all attended: no bias needed
-      const int slow_end = live ? p.S_pad : 0;
+      const int slow_end = live ? s_meta[4 + vs] : 0;        // keys beyond are all masked
       mbar_wait(&s_ready[g], n & 1, 28);
       tc_fence_after();
       ATC_TRACE(u, EV_SM_START);

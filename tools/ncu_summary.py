@@ -34,7 +34,7 @@ for r in rows[2:]:
         continue
     name = r[col["Kernel Name"]]
     m = re.search(r"(\w+)<([^>]*)>", name) or re.search(r"(\w+)\(", name) or re.search(r"(\w+)", name)
-    short = m.group(0).rstrip("(")
+    short = m.group(0).rstrip("(").replace(", ", " ")  # template arguments: "gemm2_kernel<1 0 1>" = <epilogue, bf16, full row tiles>
     dur = scaled(r, "gpu__time_duration.sum", "us")
     rd, wr = scaled(r, "dram__bytes_read.sum", "Mbyte"), scaled(r, "dram__bytes_write.sum", "Mbyte")
     print(f"{short},{r[col['Grid Size']].replace(',', ' ')},{r[col['Block Size']].replace(',', ' ')},{num(r, 'launch__registers_per_thread'):.0f},"
