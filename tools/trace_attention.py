@@ -32,12 +32,11 @@ torch.cuda.synchronize()
 L.keepb200_debug_attention_trace(None)
 t = buf.view(64, 16).cpu()
 t0 = int(t[0, 0])
-names = ["S_issue", "sm_start", "sm_half", "sm_end", "PVa_start", "PVa_end", "PVb_start", "PVb_end", "out_start", "out_done"]
+names = ["S_issue", "PV_waited", "PV_issued", "sm_start", "sm_p1", "sm_baton", "sm_end", "out_start", "out_done"]
 print("unit " + " ".join(n.rjust(10) for n in names))
 for u in range(24):
     print(f"{u:4d} " + " ".join(str(int(t[u, e]) - t0).rjust(10) for e in range(len(names))))
 d = (t[8:40] - t0).double()
 print("steady state per unit (cycles): S_issue -> S_issue of the next unit", float((d[1:, 0] - d[:-1, 0]).mean()),
-      " S_issue -> softmax start", float((d[:, 1] - d[:, 0]).mean()), " softmax (start->end)", float((d[:, 3] - d[:, 1]).mean()),
-      " softmax end -> PV tail issued", float((d[:, 7] - d[:, 3]).mean()), " PV tail issued -> O drained", float((d[:, 9] - d[:, 7]).mean()),
-      " O drained -> S(u+2) issued", float((d[2:, 0] - d[:-2, 9]).mean()), " early PV (start->end)", float((d[:, 5] - d[:, 4]).mean()))
+      " S_issue -> softmax start", float((d[:, 3] - d[:, 0]).mean()), " softmax (start->end)", float((d[:, 6] - d[:, 3]).mean()),
+      " softmax end -> PV issued", float((d[:, 2] - d[:, 6]).mean()), " PV issued -> O drained", float((d[:, 8] - d[:, 2]).mean()))
