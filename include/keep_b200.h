@@ -186,7 +186,9 @@ size_t keepb200_prompt_scores_workspace_bytes(int64_t N, int64_t D, int64_t K, i
 /* refine_seg (detection_utils.py:39-74 et al.): coords int64 [N,2] (x,y), probs fp32 [N,C].
  * First occurrence of a coordinate wins; with overlap != 0 every kept tile's probabilities are replaced by
  * the mean over the present tiles among (x-ps,y-ps),(x,y-ps),(x-ps,y),(x,y).
- * keep[N] uint8 = 1 for first occurrences; refined[N,C] fp32 (rows with keep==0 are zero). */
+ * keep[N] uint8 = 1 for first occurrences; refined[N,C] fp32 (rows with keep==0 are zero).
+ * Coordinates must lie in [-2^31, 2^31 - 2] (negative ones are ordinary keys, as in the reference's dict); a tile outside
+ * that range is never stored (keep = 0) - the caller checks the range (keep_b200/ops.py::refine does, one host read). */
 int keepb200_refine(const int64_t* coords, const float* probs, int64_t N, int64_t C, int64_t patch_size, int overlap,
                     uint8_t* keep, float* refined, void* workspace, size_t workspace_bytes, void* stream);
 size_t keepb200_refine_workspace_bytes(int64_t N);

@@ -17,9 +17,14 @@ namespace {
 
 constexpr unsigned long long kEmpty = 0xFFFFFFFFFFFFFFFFull;
 
+// Key of a coordinate: both components biased by 2^31 into 32 bits each. Coordinates in [-2^31, 2^31 - 2] (negative ones
+// included: the reference's dict keeps a tile at (-1,-1) like any other) map to distinct keys, none of which is kEmpty;
+// anything outside that range has no key (kEmpty: "absent" for a lookup, e.g. a neighbour x - ps below the range) - the
+// Python front end refuses such tile coordinates before the call (keep_b200/ops.py::refine), the C entry point documents it.
 __device__ __forceinline__ unsigned long long pack_xy(long long x, long long y) {
-  return (static_cast<unsigned long long>(static_cast<unsigned int>(x)) << 32) |
-         static_cast<unsigned long long>(static_cast<unsigned int>(y));
+  const long long lo = -2147483648ll, hi = 2147483646ll;
+  if (x < lo || x > hi || y < lo || y > hi) return kEmpty;
+  return (static_cast<unsigned long long>(x - lo) << 32) | static_cast<unsigned long long>(y - lo);
 }
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
   z ^= z >> 33; z *= 0xff51afd7ed558ccdull;
@@ -38,6 +43,7 @@ __global__ void table_insert_kernel(const long long* __restrict__ coords, long l
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const unsigned long long key = pack_xy(coords[2 * i], coords[2 * i + 1]);
+  if (key == kEmpty) return;  // outside the supported range: never stored (keep = 0 for it; refused by the front end)
   long long slot = (long long)(mix64(key) & (unsigned long long)mask);
   while (true) {
     const unsigned long long prev = atomicCAS(&keys[slot], kEmpty, key);
@@ -51,7 +57,7 @@ __global__ void table_insert_kernel(const long long* __restrict__ coords, long l
 
 __device__ __forceinline__ long long table_find(const unsigned long long* keys, const long long* vals, long long mask,
                                                 unsigned long long key) {
-  if (key == kEmpty) return -1;  // (-1,-1) is never a tile coordinate
+  if (key == kEmpty) return -1;  // no key: outside the coordinate range
   long long slot = (long long)(mix64(key) & (unsigned long long)mask);
   while (true) {
     const unsigned long long k = keys[slot];

@@ -294,6 +294,12 @@ def refine(coords, probs, patch_size, overlap):
     coords = coords.contiguous().long()
     probs = probs.contiguous().float()
     N, Cc = probs.shape
+    if N > 0:
+        # the hash key holds 32 bits per component (csrc/refine.cu::pack_xy): level-0 pixel coordinates are far inside, a
+        # coordinate outside would be silently dropped, so it is refused (one 16-byte host read per slide)
+        lo, hi = (int(v) for v in torch.aminmax(coords))
+        if lo < -(2 ** 31) or hi > 2 ** 31 - 2:
+            raise ValueError(f"refine: tile coordinates outside [-2^31, 2^31 - 2] (min {lo}, max {hi})")
     keep = torch.empty(N, dtype=torch.uint8, device=probs.device)
     refined = torch.empty(N, Cc, dtype=torch.float32, device=probs.device)
     L = _lib.lib()

@@ -522,6 +522,21 @@ def test_empty_and_single_element_inputs():
     one = torch.softmax(torch.randn(1, 2, device=DEV, generator=g), 1)
     keep, refined = ops.refine(torch.tensor([[448, 224]], device=DEV), one, 224, True)
     assert keep.tolist() == [1] and torch.equal(refined, one)  # a lone tile is its own neighbourhood
+    # negative coordinates are ordinary dict keys in the reference ((-1,-1) included); beyond 32 bits per component: refused
+    import numpy as np
+    from oracle import wsi_oracle as wo
+    xy = torch.tensor([[-1, -1], [223, 223], [-1, 223], [-225, -225], [-1, -1], [2 ** 31 - 2, 5], [-2 ** 31, 5]])
+    pr = torch.rand(7, 2)
+    keep, refined = ops.refine(xy.to(DEV), pr.to(DEV), 224, True)
+    exp = wo.refine_mean(pr.numpy(), xy.numpy(), 224, True)
+    assert keep.tolist() == [1, 1, 1, 1, 0, 1, 1]
+    got = refined.cpu().numpy()
+    for i in (0, 1, 2, 3, 5, 6):
+        assert np.array_equal(got[i], exp[tuple(xy[i].tolist())]), xy[i]
+    with pytest.raises(ValueError):
+        ops.refine(torch.tensor([[2 ** 31 - 1, 0]], device=DEV), one, 224, True)
+    with pytest.raises(ValueError):
+        ops.refine(torch.tensor([[0, -2 ** 31 - 1]], device=DEV), one, 224, True)
     x = torch.randn(1, 768, device=DEV, generator=g)
     lg, pr = ops.similarity(x, cls[:, :1].contiguous())        # one tile x one prompt
     assert lg.shape == (1, 1) and abs(pr.item() - 1.0) < 1e-6
