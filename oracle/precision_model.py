@@ -44,6 +44,10 @@ class Policy:
 
 def linear(pol, name, x, w, b):
     how = pol.lin_rule(name)
+    if how == "w":  # weights split (exact to ~2^-22), activations rounded: two MMA passes, Ah*Wh + Ah*Wl
+        return F.linear(pol.op(x, "r"), pol.op(w, "s"), b)
+    if how == "a":  # activations split, weights rounded
+        return F.linear(pol.op(x, "s"), pol.op(w, "r"), b)
     return F.linear(pol.op(x, how), pol.op(w, how), b)
 
 
@@ -133,6 +137,7 @@ def row_rel(a, b):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--bf16", action="store_true")
+    ap.add_argument("--only", default="", help="run only the policies whose name contains this string")
     args = ap.parse_args()
     dt = torch.bfloat16 if args.bf16 else torch.float16
     torch.set_num_threads(os.cpu_count() or 1)
@@ -150,7 +155,15 @@ def main():
             "all GEMMs split, attention rounded": Policy(dt, lambda n: "s"),
             "all GEMMs split, attention rounded, context hi+lo": Policy(dt, lambda n: "s", attn_out_split=True),
             "only attention rounded, exact GEMMs": Policy(dt, lambda n: "x"),
+            # two-pass candidates for a level between FAST and HIGH (the fp32 head and the split CLS tail are kept)
+            "W split everywhere, A rounded (2 passes)": Policy(dt, lambda n: "x" if n.startswith("head") else "w"),
+            "A split everywhere, W rounded (2 passes)": Policy(dt, lambda n: "x" if n.startswith("head") else "a"),
+            "W split in fc1/fc2 only": Policy(dt, lambda n: "x" if n.startswith("head") else ("w" if ".fc" in n else "r")),
+            "W split in fc2 only": Policy(dt, lambda n: "x" if n.startswith("head") else ("w" if ".fc2" in n else "r")),
+            "fc1/fc2 fully split, rest rounded": Policy(dt, lambda n: "x" if n.startswith("head") else ("s" if ".fc" in n else "r")),
         }
+        if args.only:
+            policies = {k: v for k, v in policies.items() if args.only in k}
         for name, pol in policies.items():
             ri = row_rel(vit_forward(model, pol, tiles), ref_i)
             rt = row_rel(bert_forward(model, pol, text), ref_t)
