@@ -64,6 +64,9 @@ extern "C" {
  *   HIGH: split-operand GEMMs: activations and weights are carried as hi + lo 16-bit pairs and every GEMM makes three
  *         passes into the same fp32 accumulator (Ah.Wh + Al.Wh + Ah.Wl): ~2.6e-4 / ~3e-4 rel-L2, at three times the MMA
  *         work. What stays 16-bit is the attention's q, k, v and probabilities.
+ *   BALANCED: the weights as hi + lo pairs, every activation as ONE 16-bit value, two passes (Ah.Wh + Ah.Wl): the weights'
+ *         share of the operand rounding is gone (~7e-4 image / ~8e-4 text, i.e. inside 1e-3 with margin) at twice the MMA
+ *         work instead of three times; LayerNorms run as stand-alone kernels (the folded weights exist in one 16-bit copy).
  *   AUTO: HIGH when the call is small enough for the extra passes not to matter - at most
  *         KEEPB200_IMAGE_AUTO_MAX_TILES tiles (quick-start / interactive use: latency-bound either way) or
  *         KEEPB200_TEXT_AUTO_MAX_PROMPTS prompts (every WSI classifier bank) - FAST otherwise. A function of the call's
@@ -71,6 +74,7 @@ extern "C" {
 #define KEEPB200_PRECISION_AUTO 0
 #define KEEPB200_PRECISION_HIGH 1
 #define KEEPB200_PRECISION_FAST 2
+#define KEEPB200_PRECISION_BALANCED 3
 #define KEEPB200_IMAGE_AUTO_MAX_TILES 16
 #define KEEPB200_TEXT_AUTO_MAX_PROMPTS 8192
 

@@ -93,7 +93,7 @@ SIGNATURES = {
 }
 
 ABI_VERSION = 2  # KEEPB200_ABI_VERSION of include/keep_b200.h
-PRECISION = {"auto": 0, "high": 1, "fast": 2}  # KEEPB200_PRECISION_*
+PRECISION = {"auto": 0, "high": 1, "fast": 2, "balanced": 3}  # KEEPB200_PRECISION_*
 
 _LIB = None
 

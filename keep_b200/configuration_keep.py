@@ -27,7 +27,8 @@ class KEEPConfig(PretrainedConfig):
         # keep_b200 extensions.  operand_dtype: 16-bit type of the tensor-core operands ("float16" | "bfloat16").
         # text_precision / image_precision (include/keep_b200.h KEEPB200_PRECISION_*): "high" = split-operand GEMMs
         # through the whole tower (hi + lo 16-bit pairs, three MMA passes: ~3e-4 rel-L2 against the fp32 reference),
-        # "fast" = one pass (~1.0-1.4e-3: the fp16 operand rounding; the throughput path), "auto" = high for calls of up
+        # "fast" = one pass (~1.0-1.4e-3: the fp16 operand rounding; the throughput path), "balanced" = two passes (hi + lo
+        # weights, activations rounded once: ~7e-4, inside the 1e-3 target at twice the MMA work), "auto" = high for calls of up
         # to 8192 prompts (every WSI classifier bank) / 16 tiles (quick-start use), fast for anything larger.
         self.operand_dtype = operand_dtype
         self.text_precision = text_precision

@@ -358,8 +358,13 @@ int dump_layer(Model* m, int index, size_t slot_floats, const float* src, size_t
   return KB_OK;
 }
 
-int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, int gh, int gw, bool high, float* out, char* ws,
+// precision level of a call: LEVEL_FAST one MMA pass per GEMM, LEVEL_BALANCED two (hi|lo weights, one 16-bit value per
+// activation: Ah.Wh + Ah.Wl - the weights' share of the operand rounding is gone), LEVEL_HIGH three (hi|lo both sides)
+enum { LEVEL_FAST = 0, LEVEL_HIGH = 1, LEVEL_BALANCED = 2 };
+
+int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, int gh, int gw, int level, float* out, char* ws,
                        cudaStream_t st) {
+  const bool high = level == LEVEL_HIGH, wsplit = level == LEVEL_BALANCED;
   const KeepB200Config& c = m->cfg;
   const int bf = c.operand_dtype, D = c.vit_width, F = c.vit_mlp, T = gh * gw + 1;
   const int M = (int)(n * T);
@@ -392,6 +397,9 @@ int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, int g
   if (high)
     KB_TRY(G(hid, m->pe_hl, (int)(n * (T - 1)), D, 768, EPI_PATCH_F32, bf, x, D).bias(m->pe_b).patch(pos, T - 1)
                .pitch(1536, 1536).split(GEMM_SPLIT_AW).run(st));
+  else if (wsplit)
+    KB_TRY(G(hid, m->pe_hl, (int)(n * (T - 1)), D, 768, EPI_PATCH_F32, bf, x, D).bias(m->pe_b).patch(pos, T - 1)
+               .pitch(768, 1536).split(GEMM_SPLIT_W).run(st));
   else
     KB_TRY(G(hid, m->pe_w, (int)(n * (T - 1)), D, 768, EPI_PATCH_F32, bf, x, D).bias(m->pe_b).patch(pos, T - 1).run(st));
   for (int i = 0; i < c.vit_depth; ++i) {
@@ -401,6 +409,10 @@ int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, int g
       // operands; what stays 16-bit is the attention (q, k, v, P and the context) - oracle/precision_model.py
       KB_TRY(launch_layernorm(x, D, M, D, b.n1w, b.n1b, c.vit_ln_eps, xn, bf, nullptr, st, 2 * D, D));
       KB_TRY(G(xn, b.qkv_hl, M, 3 * D, D, EPI_BIAS_HALF, bf, qkv, 3 * D).bias(b.qkv_b).pitch(2 * D, 2 * D).split(GEMM_SPLIT_AW).run(st));
+    } else if (wsplit) {
+      // two-pass path: the un-folded hi|lo weights against LayerNorm rows rounded once (stand-alone LayerNorm kernels)
+      KB_TRY(launch_layernorm(x, D, M, D, b.n1w, b.n1b, c.vit_ln_eps, xn, bf, nullptr, st));
+      KB_TRY(G(xn, b.qkv_hl, M, 3 * D, D, EPI_BIAS_HALF, bf, qkv, 3 * D).bias(b.qkv_b).pitch(D, 2 * D).split(GEMM_SPLIT_W).run(st));
     } else if (fuse >= 1 && i > 0) {
       KB_TRY(gemm_ln(xn, D, b.qkv_wf, M, 3 * D, EPI_LN_BIAS_HALF, bf, b.qkv_c, b.qkv_s, stats, c.vit_ln_eps, qkv, st));
     } else {
@@ -416,6 +428,13 @@ int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, int g
                  .split(GEMM_SPLIT_AW).lo(F).run(st));
       KB_TRY(G(hid, b.fc2_hl, M, D, F, EPI_RESID_F32, bf, x, D).bias(b.fc2_b).gamma(b.ls2).resid(x).pitch(2 * F, 2 * F)
                  .split(GEMM_SPLIT_AW).run(st));
+    } else if (i + 1 < c.vit_depth && wsplit) {
+      KB_TRY(G(att, b.proj_hl, M, D, D, EPI_RESID_F32, bf, x, D).bias(b.proj_b).gamma(b.ls1).resid(x).pitch(D, 2 * D)
+                 .split(GEMM_SPLIT_W).run(st));
+      KB_TRY(launch_layernorm(x, D, M, D, b.n2w, b.n2b, c.vit_ln_eps, xn, bf, nullptr, st));
+      KB_TRY(G(xn, b.fc1_hl, M, F, D, EPI_BIAS_GELU_HALF, bf, hid, F).bias(b.fc1_b).pitch(D, 2 * D).split(GEMM_SPLIT_W).run(st));
+      KB_TRY(G(hid, b.fc2_hl, M, D, F, EPI_RESID_F32, bf, x, D).bias(b.fc2_b).gamma(b.ls2).resid(x).pitch(F, 2 * F)
+                 .split(GEMM_SPLIT_W).run(st));
     } else if (i + 1 < c.vit_depth && fuse == 2) {
       KB_TRY(gemm_resid_stats(att, b.proj_w, M, D, D, bf, b.proj_b, b.ls1, x, xn, stats, st));
       KB_TRY(gemm_ln(xn, D, b.fc1_wf, M, F, EPI_LN_BIAS_GELU_HALF, bf, b.fc1_c, b.fc1_s, stats, c.vit_ln_eps, hid, st));
@@ -453,7 +472,8 @@ int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, int g
 // precise: every GEMM of the tower runs split-operand on hi|lo activations and weights (3 MMA passes, ~22-bit operands);
 // what is left of the 16-bit rounding is the attention's q/k/v/P (see oracle/precision_model.py)
 int encode_text_chunk(Model* m, const int64_t* ids, const int64_t* tts, const int64_t* mask, int64_t n, int64_t S,
-                      int64_t se, bool precise, float* out, char* ws, cudaStream_t st) {
+                      int64_t se, int level, float* out, char* ws, cudaStream_t st) {
+  const bool precise = level == LEVEL_HIGH;
   const KeepB200Config& c = m->cfg;
   const int bf = c.operand_dtype, d = c.hidden, I = c.intermediate;
   const int M = (int)(n * se);
@@ -465,7 +485,7 @@ int encode_text_chunk(Model* m, const int64_t* ids, const int64_t* tts, const in
   void* hid = ws + w.hid;
   float* xc32 = reinterpret_cast<float*>(ws + w.xc32);
   void* xc16 = ws + w.xc16;
-  const int sp = precise ? GEMM_SPLIT_AW : GEMM_SPLIT_NONE;
+  const int sp = precise ? GEMM_SPLIT_AW : level == LEVEL_BALANCED ? GEMM_SPLIT_W : GEMM_SPLIT_NONE;
   const int gelu = precise ? EPI_BIAS_GELU_HILO : EPI_BIAS_GELU_HALF;
   const int64_t lo_d = precise ? d : 0, lo_I = precise ? I : 0;  // offsets of the lo halves (0 = not written)
   KB_TRY(launch_bert_embed(ids, tts, S, n, (int)se, d, m->word, m->ttype, m->tpos, m->emb_lnw, m->emb_lnb,
@@ -666,10 +686,11 @@ int keepb200_encode_image_hw(void* handle, const void* tiles, int layout, int64_
   if (B < 0 || !tiles || !out) return set_error(KB_ERR_ARG, "encode_image: bad arguments");
   if (layout != KEEPB200_TILES_F32_NCHW && layout != KEEPB200_TILES_U8_NHWC)
     return set_error(KB_ERR_ARG, "encode_image: unknown tile layout %d", layout);
-  if (precision != KEEPB200_PRECISION_AUTO && precision != KEEPB200_PRECISION_HIGH && precision != KEEPB200_PRECISION_FAST)
+  if (precision < KEEPB200_PRECISION_AUTO || precision > KEEPB200_PRECISION_BALANCED)
     return set_error(KB_ERR_ARG, "encode_image: unknown precision %d", precision);
   // AUTO is a function of the call's tile count only (never of the workspace or the chunking)
   const bool high = keepb200_image_precision_is_high(precision, B) != 0;
+  const int level = high ? LEVEL_HIGH : precision == KEEPB200_PRECISION_BALANCED ? LEVEL_BALANCED : LEVEL_FAST;
   int gh, gw;
   KB_TRY(check_hw(m, H, W, &gh, &gw));
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return set_error(KB_ERR_ARG, "encode_image: workspace must be 1024-byte aligned");
@@ -690,7 +711,7 @@ int keepb200_encode_image_hw(void* handle, const void* tiles, int layout, int64_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int64_t b0 = 0; b0 < B; b0 += chunk) {
     const int64_t n = (B - b0 < chunk) ? (B - b0) : chunk;
-    KB_TRY(encode_image_chunk(m, static_cast<const char*>(tiles) + (size_t)b0 * tile_bytes, layout, n, gh, gw, high,
+    KB_TRY(encode_image_chunk(m, static_cast<const char*>(tiles) + (size_t)b0 * tile_bytes, layout, n, gh, gw, level,
                               out + (size_t)b0 * m->cfg.proj_dim, static_cast<char*>(workspace), st));
   }
   return KB_OK;
@@ -716,10 +737,11 @@ int keepb200_encode_text(void* handle, const int64_t* ids, const int64_t* type_i
     return set_error(KB_ERR_ARG, "encode_text: sequence length %lld outside [1, %d]", (long long)S,
                      m->cfg.max_pos < 512 ? m->cfg.max_pos : 512);
   if (s_eff < 1 || s_eff > S) return set_error(KB_ERR_ARG, "encode_text: s_eff %lld outside [1, %lld]", (long long)s_eff, (long long)S);
-  if (precision != KEEPB200_PRECISION_AUTO && precision != KEEPB200_PRECISION_HIGH && precision != KEEPB200_PRECISION_FAST)
+  if (precision < KEEPB200_PRECISION_AUTO || precision > KEEPB200_PRECISION_BALANCED)
     return set_error(KB_ERR_ARG, "encode_text: unknown precision %d", precision);
   // AUTO is a function of the call's prompt count only (never of the workspace or the chunking)
   const bool precise = precision == KEEPB200_PRECISION_HIGH || (precision == KEEPB200_PRECISION_AUTO && P <= KEEPB200_TEXT_AUTO_MAX_PROMPTS);
+  const int level = precise ? LEVEL_HIGH : precision == KEEPB200_PRECISION_BALANCED ? LEVEL_BALANCED : LEVEL_FAST;
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return set_error(KB_ERR_ARG, "encode_text: workspace must be 1024-byte aligned");
   const size_t per1 = text_ws(m, 1, s_eff).total;
   if (!workspace || workspace_bytes < per1)
@@ -735,7 +757,7 @@ int keepb200_encode_text(void* handle, const int64_t* ids, const int64_t* type_i
   for (int64_t p0 = 0; p0 < P; p0 += chunk) {
     const int64_t n = (P - p0 < chunk) ? (P - p0) : chunk;
     KB_TRY(encode_text_chunk(m, ids + p0 * S, type_ids ? type_ids + p0 * S : nullptr, mask ? mask + p0 * S : nullptr, n, S,
-                             s_eff, precise, out + (size_t)p0 * m->cfg.hidden, static_cast<char*>(workspace), st));
+                             s_eff, level, out + (size_t)p0 * m->cfg.hidden, static_cast<char*>(workspace), st));
   }
   return KB_OK;
 }

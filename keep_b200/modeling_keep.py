@@ -196,7 +196,7 @@ class KEEPModel(PreTrainedModel):
             return out
         precision = _lib.PRECISION.get(str(getattr(self.config, "image_precision", "auto")))
         if precision is None:
-            raise ValueError(f"image_precision must be 'auto', 'high' or 'fast', got {self.config.image_precision!r}")
+            raise ValueError(f"image_precision must be 'auto', 'high', 'balanced' or 'fast', got {self.config.image_precision!r}")
         L = _lib.lib()
         with torch.cuda.device(dev):
             high = L.keepb200_image_precision_is_high(precision, B)
@@ -231,7 +231,7 @@ class KEEPModel(PreTrainedModel):
             return out
         precision = _lib.PRECISION.get(str(getattr(self.config, "text_precision", "auto")))
         if precision is None:
-            raise ValueError(f"text_precision must be 'auto', 'high' or 'fast', got {self.config.text_precision!r}")
+            raise ValueError(f"text_precision must be 'auto', 'high', 'balanced' or 'fast', got {self.config.text_precision!r}")
         s_eff = S
         if mask is not None:
             mask = mask.to(device=dev, dtype=torch.long).contiguous()

@@ -11,6 +11,8 @@ Tolerance (north_star: 1e-3 relative): per-embedding rel-L
   * FAST - one MMA pass over fp16 operands, the throughput path (bulk tiles, prompt banks): FAST_REL_IMAGE = 1.25e-3
     (measured 1.0-1.2e-3: the inherent 2^-11 rounding of 24 x 4 GEMM operand pairs; torch's own fp16 autocast of this
     ViT-L lands at 1.2e-3) and FAST_REL_TEXT = 2e-3 (measured ~1.4e-3: post-LN BERT has no LayerScale to damp it).
+  * BALANCED - two passes (hi + lo weights, one 16-bit value per activation): BAL_REL_IMAGE = 9e-4, BAL_REL_TEXT = 1e-3
+    (oracle/precision_model.py: 6.2e-4 / 7.1e-4 emulated) - the cheapest level whose gate is the north star itself.
 bf16 operands are reported against a looser 2e-2 (3 fewer mantissa bits; torch's own bf16 autocast lands at ~1e-2)."""
 import numpy as np
 import pytest
@@ -22,6 +24,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 NORTH_STAR = 1e-3
 HIGH_REL_IMAGE, HIGH_REL_TEXT, FAST_REL_IMAGE, FAST_REL_TEXT, FP16_COS, SIM_ABS = 5e-4, 7.5e-4, 1.25e-3, 2e-3, 0.99999, 1e-3
+BAL_REL_IMAGE, BAL_REL_TEXT = 9e-4, NORTH_STAR
 IMAGE_REL, TEXT_REL = HIGH_REL_IMAGE, HIGH_REL_TEXT  # what the default ("auto") policy delivers at these batch sizes
 HIGH_REL = HIGH_REL_IMAGE
 FAST_REL = FAST_REL_TEXT
@@ -242,6 +245,38 @@ def test_text_precision_modes(full_pair):
         assert common.row_metrics(one, res["auto"][i:i + 1])[0] < 2.5e-4, i
 
 
+def test_balanced_precision_level(full_pair, golden_dir):
+    """image_precision / text_precision = "balanced": hi|lo weights against one 16-bit value per activation (two MMA passes,
+    stand-alone LayerNorms). Config 1 inputs plus a 40-tile batch (chunked: batch invariance inside the level); the gate is
+    the north star's 1e-3, and the level must sit between FAST and HIGH."""
+    oracle, prod, _ = full_pair
+    g = common.load_golden(golden_dir, "keep_full.npz")
+    tiles, text = common.full_inputs(torch.from_numpy(g["example_tile_f16"]))
+    gen = torch.Generator().manual_seed(77)
+    more = torch.randn(40, 3, 224, 224, generator=gen)
+    with torch.no_grad():
+        ref_i, ref_t = oracle.encode_image(torch.cat([tiles, more[:2]])), oracle.encode_text(text)
+    res = {}
+    for mode in ("fast", "balanced", "high"):
+        with precision(prod, image=mode, text=mode):
+            img = prod.encode_image(torch.cat([tiles, more]).to(DEV)).cpu()
+            txt = prod.encode_text(common.to_device(text, DEV)).cpu()
+            res[mode] = (common.row_metrics(img[:ref_i.shape[0]], ref_i)[0], common.row_metrics(txt, ref_t)[0])
+            if mode == "balanced":
+                alone = prod.encode_image(tiles.to(DEV)).cpu()
+                assert torch.equal(alone, img[:tiles.shape[0]])  # the level does not depend on the batch
+                old_chunk = prod.image_chunk
+                prod.image_chunk = 16
+                try:
+                    assert torch.equal(prod.encode_image(torch.cat([tiles, more]).to(DEV)).cpu(), img)
+                finally:
+                    prod.image_chunk = old_chunk
+    print("rel-L2 (image, text) per level:", {k: (f"{a:.2e}", f"{b:.2e}") for k, (a, b) in res.items()})
+    assert res["balanced"][0] <= BAL_REL_IMAGE and res["balanced"][1] <= BAL_REL_TEXT
+    assert res["high"][0] < res["balanced"][0] < res["fast"][0]
+    assert res["high"][1] < res["balanced"][1] < res["fast"][1]
+
+
 def test_per_layer_parity_table(full_pair, golden_dir):
     """Where the error comes from: the residual stream after every ViT block / BERT layer (config 1) against the
     activations of the reference class itself (tests/golden/keep_full_layers.npz, oracle/make_golden.py)."""
@@ -250,7 +285,8 @@ def test_per_layer_parity_table(full_pair, golden_dir):
     gl = common.load_golden(golden_dir, "keep_full_layers.npz")
     tiles, text = common.full_inputs(torch.from_numpy(g["example_tile_f16"]))
     it, tt = gl["image_tokens"].tolist(), gl["text_tokens"].tolist()
-    for mode, gate_i, gate_t in (("fast", FAST_REL_IMAGE, FAST_REL_TEXT), ("high", HIGH_REL_IMAGE, HIGH_REL_TEXT)):
+    for mode, gate_i, gate_t in (("fast", FAST_REL_IMAGE, FAST_REL_TEXT), ("balanced", BAL_REL_IMAGE, BAL_REL_TEXT),
+                                 ("high", HIGH_REL_IMAGE, HIGH_REL_TEXT)):
         with precision(prod, image=mode, text=mode):
             vis, img = prod.debug_layer_outputs(image_inputs=tiles.to(DEV))
             txt_layers, txt = prod.debug_layer_outputs(text_inputs=common.to_device(text, DEV))
