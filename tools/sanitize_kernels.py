@@ -32,6 +32,11 @@ ops.gemm_resid_stats(a, w, resid.clone(), bias=bias)
 x32, w32 = rn(300, 128), rn(256, 128) * 0.1
 h = ops.gemm_split(ops.cast_hilo(x32), ops.cast_hilo(w32), 128, ops.EPI_BIAS_GELU_HILO, ops.SPLIT_AW, bias=bias)
 assert (h[:, :256].float() + h[:, 256:].float() - F.gelu(x32 @ w32.T + bias)).abs().max() < 1e-3
+# BALANCED level: hi|lo weights against plain 16-bit activations on the CTA-pair kernel (two passes over K), GELU epilogue
+whl = ops.cast_hilo(w32)
+a16 = (rn(256 * 150, 128) * 0.5).half()
+h2 = ops.gemm_split(a16, whl, 128, ops.EPI_BIAS_GELU_HALF, ops.SPLIT_W, bias=bias)
+assert (h2.float() - F.gelu(a16.float() @ w32.T + bias)).abs().max() < 5e-3
 ab, wb = a[: 256 * 80 + 37].bfloat16(), w.bfloat16()                           # ragged row tiles, bf16 epilogue variants
 ops.gemm(ab, wb, ops.EPI_BIAS_GELU_HALF, bias=bias)
 for B, S, H, masked in ((4, 197, 2, False), (40, 12, 2, True), (2, 300, 2, True), (3, 100, 2, True), (3, 256, 2, True), (2, 240, 2, False)):
@@ -51,5 +56,8 @@ assert (lg - F.normalize(big, dim=-1) @ cls128).abs().max() < 1e-3 and (pr.view(
 ops.prompt_scores(feats, F.normalize(rn(768, 64), dim=0), 16, 4, fused=True)
 ops.visual_head(rn(20, 1024), torch.ones(1024, device=dev), torch.zeros(1024, device=dev), 1e-6, rn(768, 1024) / 32, rn(768), rn(768, 768) / 27, rn(768))
 ops.pooler(rn(5, 768), rn(768, 768) / 27, rn(768))
+xy = torch.tensor([[-1, -1], [223, 223], [-1, 223], [-225, -225], [-1, -1], [2 ** 31 - 2, 5], [-2 ** 31, 5]], device=dev)
+keep, _ = ops.refine(xy, torch.rand(7, 2, device=dev, generator=g), 224, True)   # biased 32-bit keys, negative coordinates
+assert keep.tolist() == [1, 1, 1, 1, 0, 1, 1]
 torch.cuda.synchronize()
 print("sanitize_kernels: all launches completed")
