@@ -135,6 +135,25 @@ def cpu_reference_tiles_per_s(sample_tiles: int, steps: int, warmup: int):
     return sample_tiles / sec, sec * 1e3, threads, cpu_name
 
 
+def cpu_reference_prompts_per_s(sample_prompts: int = 8, iters: int = 2):
+    """encode_text on the CPU for `sample_prompts` padded prompts (S = 256, batch 8 as in SURVEY.md section 8d), fp32."""
+    from oracle import keep_oracle as ko  # CPU baseline leg
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = ko.KEEPModel(ko.DEFAULT_TEXT_CONFIG, 768, ko.DEFAULT_VISION_CONFIG).eval()
+    model.load_state_dict(ko.synthetic_state_dict(model, seed=0))
+    text = ko.synthetic_text_inputs(sample_prompts, seq_len=256, seed=3000)
+    times = []
+    with torch.no_grad():
+        for i in range(iters + 1):
+            t0 = time.perf_counter()
+            _ = float(model.encode_text(text).sum())
+            if i >= 1:
+                times.append(time.perf_counter() - t0)
+    return sample_prompts / (sum(times) / len(times)), threads
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return 0
@@ -541,6 +560,11 @@ def main():
         tps, ms_cpu, threads, cpu = cpu_reference_tiles_per_s(32, steps=2, warmup=1)
         cpu_baseline = {"value": tps, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"32 tiles per iteration x 2 timed iterations (1 warm-up), encode_image + similarity, fp32, {cpu}"}
+        if extra and "config5_prompt_bank" in extra:  # the text tower's CPU figure beside config 5
+            pps, pthreads = cpu_reference_prompts_per_s()
+            extra["config5_prompt_bank"]["cpu_baseline"] = {
+                "value": pps, "unit": "prompts/s", "cores": pthreads, "kind": "port",
+                "sample": "8 prompts padded to seq_len 256 per iteration x 2 timed iterations (1 warm-up), encode_text, fp32"}
 
     if rank == 0:
         peaks = measured_peaks()
