@@ -62,6 +62,9 @@ class KEEPModel(PreTrainedModel):
         self._handle_device = None
         self._dirty = True
         self._ws = None
+        # transformers' own bookkeeping (tied-weight tables etc.): `from_pretrained(<local release dir>)` needs it on
+        # transformers >= 5; `_init_weights` is a no-op here, weights always come from a state-dict
+        self.post_init()
 
     # ---- checkpoint plumbing -------------------------------------------------------------------------
     def _init_weights(self, module):  # weights always come from a state-dict

@@ -245,6 +245,19 @@ def test_text_precision_modes(full_pair):
         assert common.row_metrics(one, res["auto"][i:i + 1])[0] < 2.5e-4, i
 
 
+def test_from_pretrained_model_encodes_like_the_loaded_one(tiny_pair, tmp_path):
+    """save_pretrained -> AutoModel.from_pretrained (transformers' loader, not load_state_dict) -> .to(cuda): the handle is
+    built from the loaded parameters and the embeddings equal those of the model the checkpoint came from, bit for bit."""
+    from transformers import AutoModel
+
+    _, prod, _, _ = tiny_pair
+    prod.save_pretrained(tmp_path)
+    again = AutoModel.from_pretrained(str(tmp_path)).to(DEV).eval()
+    g = torch.Generator().manual_seed(3)
+    tiles = torch.randn(3, 3, 224, 224, generator=g).to(DEV)
+    assert torch.equal(again.encode_image(tiles), prod.encode_image(tiles))
+
+
 def test_balanced_precision_level(full_pair, golden_dir):
     """image_precision / text_precision = "balanced": hi|lo weights against one 16-bit value per activation (two MMA passes,
     stand-alone LayerNorms). Config 1 inputs plus a 40-tile batch (chunked: batch invariance inside the level); the gate is

@@ -62,6 +62,29 @@ def test_save_and_reload_roundtrip(tmp_path):
     assert torch.equal(m2.state_dict()["text.pooler.dense.weight"], sd["text.pooler.dense.weight"])
 
 
+def test_from_pretrained_local_release_dir(tmp_path):
+    """README.md:49-55 of the reference: AutoModel.from_pretrained(<repo>) - here on a local directory, through
+    transformers' own loader (safetensors written by save_pretrained, and the release's pytorch_model.bin layout)."""
+    from transformers import AutoModel
+
+    cfg = KEEPConfig(text_config=ko.TINY_TEXT_CONFIG, vision_config=ko.TINY_VISION_CONFIG, projection_dim=128)
+    m = KEEPModel(cfg)
+    _, sd, _ = common.tiny_oracle(seed=5)
+    m.load_state_dict(sd)
+    m.save_pretrained(tmp_path / "st")
+    m2 = AutoModel.from_pretrained(str(tmp_path / "st"))
+    assert type(m2) is KEEPModel and m2._dirty
+    for k, v in sd.items():
+        if k in m2.state_dict():
+            assert torch.equal(m2.state_dict()[k], v), k
+    (tmp_path / "bin").mkdir()
+    cfg.save_pretrained(tmp_path / "bin")
+    torch.save(m.state_dict(), tmp_path / "bin" / "pytorch_model.bin")
+    m3 = KEEPModel.from_pretrained(str(tmp_path / "bin"))
+    assert torch.equal(m3.state_dict()["visual.blocks.1.attn.qkv.weight"], sd["visual.blocks.1.attn.qkv.weight"])
+    assert float(m3.logit_scale.detach()) == pytest.approx(3.2188758, abs=1e-6)
+
+
 def test_no_cpu_fallback():
     m = KEEPModel(KEEPConfig(text_config=ko.TINY_TEXT_CONFIG, vision_config=ko.TINY_VISION_CONFIG, projection_dim=128))
     with pytest.raises(KeepB200Error, match="no CPU fallback"):
