@@ -2,7 +2,7 @@
 vectors produced by the reference class (tests/golden, oracle/make_golden.py).
 
 Tolerance (north_star: 1e-3 relative): per-embedding rel-L2 against the fp32 oracle and cosine
->= 0.99999, similarity matrix max-abs <= 1e-3. Two precision levels exist (include/keep_b200.h KEEPB200_PRECISION_*):
+>= 0.99999, similarity matrix max-abs <= 1e-3. Three precision levels exist (include/keep_b200.h KEEPB200_PRECISION_*):
   * HIGH - split-operand GEMMs (hi + lo 16-bit operand pairs, three MMA passes). This is what the default "auto" policy
     runs for calls of quick-start / WSI-classifier size (<= 16 tiles, <= 8192 prompts): HIGH_REL_IMAGE = 5e-4 (measured
     2.0-3.4e-4), HIGH_REL_TEXT = 7.5e-4 (measured 2.7-5.0e-4 for prompts of 4-32 tokens, 7.2e-4 for a one-token prompt:
