@@ -63,7 +63,7 @@ extern "C" {
  *         autocast of the same ViT-L: 1.2e-3). This is the throughput path (tiles/s, prompt banks).
  *   HIGH: split-operand GEMMs: activations and weights are carried as hi + lo 16-bit pairs and every GEMM makes three
  *         passes into the same fp32 accumulator (Ah.Wh + Al.Wh + Ah.Wl): ~2.6e-4 / ~3e-4 rel-L2, at three times the MMA
- *         work. What stays 16-bit is the attention's q, k, v and probabilities.
+ *         work. What stays 16-bit is the attention's q, k, v and probabilities (its context output is hi + lo too).
  *   BALANCED: the weights as hi + lo pairs, every activation as ONE 16-bit value, two passes (Ah.Wh + Ah.Wl): the weights'
  *         share of the operand rounding is gone (~7e-4 image / ~8e-4 text, i.e. inside 1e-3 with margin) at twice the MMA
  *         work instead of three times; LayerNorms run as stand-alone kernels (the folded weights exist in one 16-bit copy).

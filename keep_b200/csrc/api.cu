@@ -280,7 +280,7 @@ ImageWs image_ws(const Model* m, int64_t n, int gh, int gw, bool high) {
   w.x = take(M * D * 4);
   w.xn = take(M * D * 2 * hl);
   w.qkv = take(M * 3 * D * 2);
-  w.att = take(M * D * 2);
+  w.att = take(M * D * 2 * hl);  // high: the attention context as a [M, 2D] hi|lo operand of the output projection
   size_t hid_bytes = M * F * 2 * hl;  // also holds the [n, 2F] hi|lo hidden of the CLS-row tail (T >= 2)
   if (patch_bytes > hid_bytes) hid_bytes = patch_bytes;  // the patch matrix aliases the MLP hidden buffer
   w.hid = take(hid_bytes);
@@ -419,10 +419,11 @@ int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, int g
       KB_TRY(launch_layernorm(x, D, M, D, b.n1w, b.n1b, c.vit_ln_eps, xn, bf, nullptr, st));
       KB_TRY(G(xn, b.qkv_w, M, 3 * D, D, EPI_BIAS_HALF, bf, qkv, 3 * D).bias(b.qkv_b).run(st));
     }
-    KB_TRY(launch_attention(qkv, att, (int)n, T, c.vit_heads, bf, nullptr, 0, 0.125f, st));
+    if (high) KB_TRY(launch_attention(qkv, att, (int)n, T, c.vit_heads, bf, nullptr, 0, 0.125f, st, 2 * D, D));  // context hi|lo
+    else KB_TRY(launch_attention(qkv, att, (int)n, T, c.vit_heads, bf, nullptr, 0, 0.125f, st));
     if (i + 1 < c.vit_depth && high) {
-      KB_TRY(G(att, b.proj_hl, M, D, D, EPI_RESID_F32, bf, x, D).bias(b.proj_b).gamma(b.ls1).resid(x).pitch(D, 2 * D)
-                 .split(GEMM_SPLIT_W).run(st));
+      KB_TRY(G(att, b.proj_hl, M, D, D, EPI_RESID_F32, bf, x, D).bias(b.proj_b).gamma(b.ls1).resid(x).pitch(2 * D, 2 * D)
+                 .split(GEMM_SPLIT_AW).run(st));
       KB_TRY(launch_layernorm(x, D, M, D, b.n2w, b.n2b, c.vit_ln_eps, xn, bf, nullptr, st, 2 * D, D));
       KB_TRY(G(xn, b.fc1_hl, M, F, D, EPI_BIAS_GELU_HILO, bf, hid, 2 * F).bias(b.fc1_b).pitch(2 * D, 2 * D)
                  .split(GEMM_SPLIT_AW).lo(F).run(st));
@@ -453,8 +454,12 @@ int encode_image_chunk(Model* m, const void* tiles, int layout, int64_t n, int g
       // MMA time is nothing, so these GEMMs always run split-operand (hi|lo weights, hi|lo LayerNorm / GELU outputs):
       // the tail adds no 2^-11 operand rounding of its own to the embedding.
       const int64_t pitch = (int64_t)T * D;
-      KB_TRY(G(att, b.proj_hl, (int)n, D, D, EPI_RESID_F32, bf, xc, D).bias(b.proj_b).gamma(b.ls1).resid(x, pitch)
-                 .pitch(pitch, 2 * D).split(GEMM_SPLIT_W).run(st));
+      if (high)
+        KB_TRY(G(att, b.proj_hl, (int)n, D, D, EPI_RESID_F32, bf, xc, D).bias(b.proj_b).gamma(b.ls1).resid(x, pitch)
+                   .pitch(2 * pitch, 2 * D).split(GEMM_SPLIT_AW).run(st));
+      else
+        KB_TRY(G(att, b.proj_hl, (int)n, D, D, EPI_RESID_F32, bf, xc, D).bias(b.proj_b).gamma(b.ls1).resid(x, pitch)
+                   .pitch(pitch, 2 * D).split(GEMM_SPLIT_W).run(st));
       KB_TRY(launch_layernorm(xc, D, n, D, b.n2w, b.n2b, c.vit_ln_eps, cls16, bf, nullptr, st, 2 * D, D));
       KB_TRY(G(cls16, b.fc1_hl, (int)n, F, D, EPI_BIAS_GELU_HILO, bf, hid, 2 * F).bias(b.fc1_b).pitch(2 * D, 2 * D)
                  .split(GEMM_SPLIT_AW).lo(F).run(st));
